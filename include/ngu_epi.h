@@ -1,0 +1,187 @@
+/*
+ * ngu_epi.h — C ABI of the B200 episodic-novelty engine (libngu_epi.so).
+ *
+ * This is the drop-in boundary for the per-step episodic-novelty hot path of
+ * minoring/NGU.  The reference has no FFI of its own (it is pure Python over
+ * torch eager ops), so each entry point cites the reference Python interface
+ * it replaces; paths are relative to the reference checkout.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types in any signature;
+ *   - every function returns NGU_OK (0) or a negative NGU_E* code;
+ *     ngu_epi_last_error() gives the text for the last failure on a handle
+ *     (or, with a NULL handle, for the last failed ngu_epi_create);
+ *   - pointers named *_dev are device pointers on the handle's GPU, *_host are
+ *     host pointers; `stream` is a cudaStream_t passed as void* (NULL = the
+ *     legacy default stream).  Calls that take a stream only enqueue work and
+ *     return without synchronising; *_host calls are synchronous;
+ *   - one handle per GPU / per shard of actors; a handle is not thread-safe;
+ *   - there is no CPU fallback: without a CUDA device every call fails.
+ *
+ * Data layout in HBM (owned by the handle unless `memory_dev` is supplied):
+ *   episodic memory  float [n_actors][capacity][32]   (actor-major; each
+ *   actor's ring is one contiguous stream of 128-byte rows).  The reference's
+ *   tensor is slot-major (capacity, n_actors, 32)
+ *   (episodic_novelty.py:32-33); ngu_epi_memory() returns the strides that
+ *   present this buffer as that (capacity, n_actors, 32) view.
+ */
+#ifndef NGU_EPI_H
+#define NGU_EPI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGU_EPI_ABI_VERSION 1
+#define NGU_EPI_DIM 32          /* controllable_state_dim, episodic_novelty.py:23 */
+#define NGU_EPI_MAX_K 32        /* k-NN list lives in one warp */
+
+enum {
+    NGU_OK = 0,
+    NGU_EINVAL = -1,            /* bad argument / unsupported configuration */
+    NGU_ECUDA = -2,             /* a CUDA runtime / driver call failed */
+    NGU_ENOMEM = -3,
+    NGU_ESTATE = -4             /* call order violated (e.g. finish before scan) */
+};
+
+enum {
+    NGU_MODE_REFERENCE = 0,     /* what minoring/NGU computes: k FARTHEST slots, Euclidean
+                                   (sqrt) distance, per-rank running mean */
+    NGU_MODE_PAPER = 1          /* NGU paper: k NEAREST slots, squared distance */
+};
+
+typedef struct ngu_epi ngu_epi;
+
+/* Mirrors the arguments of EpisodicNovelty.__init__ (episodic_novelty.py:9-35)
+ * and the model_hypr keys it reads (models/model_hypr.py:52-57). */
+typedef struct ngu_epi_cfg {
+    int32_t n_actors;           /* actors held by THIS handle (local shard)          */
+    int32_t capacity;           /* episodic_memory_capacity (N slots per actor)      */
+    int32_t dim;                /* must be NGU_EPI_DIM                               */
+    int32_t k;                  /* num_neighbors, 1..NGU_EPI_MAX_K, k <= capacity    */
+    int32_t mode;               /* NGU_MODE_*                                        */
+    int32_t device;             /* CUDA device ordinal                               */
+    float kernel_epsilon;       /* model_hypr['kernel_epsilon']                      */
+    float cluster_distance;     /* model_hypr['cluster_distance']                    */
+    float pseudo_counts;        /* model_hypr['kernel_pseudo_counts_constant']       */
+    float max_similarity;       /* model_hypr['kernel_maximum_similarity']           */
+    float max_reward_scale;     /* IntrinsicNovelty.max_rew = L (intrinsic_novelty.py:16) */
+    float reserved0;
+    double prior_count;         /* initial RunningMeanStd.count of ed_rms; the reference's
+                                   RunningMeanStd((k,)) makes this k (mpi_util.py:38-42) */
+    int32_t scan_ctas_per_sm;   /* 0 = default; tuning knobs, see DESIGN.md          */
+    int32_t scan_variant;       /* 0 = default                                       */
+} ngu_epi_cfg;
+
+/* Running statistics + ring cursor; checkpoint / parity injection.
+ * ed_* mirror EpisodicNovelty.ed_rms (episodic_novelty.py:28), epi_* mirror
+ * epi_novel_rms (:29), intr_* mirror IntrinsicNovelty.intrinsic_novel_rms
+ * (intrinsic_novelty.py:17); cursor mirrors memory_idx (episodic_novelty.py:34). */
+typedef struct ngu_epi_state {
+    double ed_mean[NGU_EPI_MAX_K];
+    double ed_var[NGU_EPI_MAX_K];
+    double ed_count;
+    double epi_mean, epi_var, epi_count;
+    double intr_mean, intr_var, intr_count;
+    int64_t cursor;
+    int64_t steps;              /* finished steps since create / set_state */
+} ngu_epi_state;
+
+/* Number of doubles exchanged between shards per step:
+ * [0,k) sum_b dist_j (f32-exact), [k,2k) sum_b dist_j^2, [2k] actor count. */
+#define NGU_EPI_RANK_SUMS(k) (2 * (k) + 1)
+/* Log-only sums: {sum r_epi, sum r_epi^2, sum r_int, sum r_int^2, count}. */
+#define NGU_EPI_LOG_SUMS 5
+
+int ngu_epi_abi_version(void);
+
+/* EpisodicNovelty.__init__ (episodic_novelty.py:9-35): allocates the zeroed
+ * memory (unless memory_dev != NULL: caller-owned float[n_actors*capacity*32],
+ * 128-byte aligned, must already be zeroed or hold valid rows), cursor 0,
+ * running statistics at their priors. */
+int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out);
+void ngu_epi_destroy(ngu_epi* h);
+const char* ngu_epi_last_error(const ngu_epi* h);
+
+/* EpisodicNovelty.episodic_memory (episodic_novelty.py:32-33, read by
+ * intrinsic_novelty.py:39-40): base pointer + element strides of the
+ * (capacity, n_actors, 32) view. */
+int ngu_epi_memory(ngu_epi* h, float** memory_dev, int64_t strides[3]);
+
+/* episodic_novelty.py:51-54 — distance scan over all `capacity` slots of every
+ * actor + top-k (kernel A + merge).  q_dev: float[n_actors][32], the controllable
+ * states returned by Embedding (:47).  Leaves the per-actor k-NN (d^2, slot)
+ * lists and this shard's rank sums in the handle. */
+int ngu_epi_scan(ngu_epi* h, const float* q_dev, void* stream);
+
+/* Device pointer to this shard's double[NGU_EPI_RANK_SUMS(k)], valid after
+ * ngu_epi_scan on the same stream.  This is the buffer the reference reduces
+ * with MPI.Allreduce (mpi_util.py:7-18 via episodic_novelty.py:56); with several
+ * shards, sum it across shards (NCCL) and pass the result to ngu_epi_finish. */
+int ngu_epi_rank_sums(ngu_epi* h, double** sums_dev);
+
+/* episodic_novelty.py:56-78 + intrinsic_novelty.py:26-31 — running-mean update
+ * from the (global) rank sums, normalise, cluster clamp, inverse kernel,
+ * similarity, reward, RND multiplier clipped to [1, L].
+ *   sums_global_dev  NULL = use this handle's own rank sums (single shard)
+ *   alpha_dev        float[n_actors] RND modulator (lifelong_novelty.py:57), NULL = 1
+ *   r_int_dev        float[n_actors] out: r_episodic * clip(alpha, 1, L)
+ *   r_epi_dev        float[n_actors] out or NULL: r_episodic (what
+ *                    compute_episodic_novelty returns, episodic_novelty.py:84)
+ *   log_sums_dev     double[NGU_EPI_LOG_SUMS] out or NULL: this shard's batch sums
+ *                    for the log-only statistics (see ngu_epi_log_update). */
+int ngu_epi_finish(ngu_epi* h, const double* sums_global_dev, const float* alpha_dev,
+                   float* r_int_dev, float* r_epi_dev, double* log_sums_dev, void* stream);
+
+/* episodic_novelty.py:82 + intrinsic_novelty.py:32 — log-only RunningMeanStd
+ * updates (epi_novel_rms, intrinsic_novel_rms) from (globally summed) log sums. */
+int ngu_epi_log_update(ngu_epi* h, const double* log_sums_global_dev, void* stream);
+
+/* EpisodicNovelty.insert_state (episodic_novelty.py:86-89): memory[cursor,:,:] = q;
+ * cursor = (cursor+1) % capacity.  The cursor lives on the device so the step
+ * can be replayed from a CUDA graph. */
+int ngu_epi_append(ngu_epi* h, const float* q_dev, void* stream);
+
+/* IntrinsicNovelty.reset_memory_if_done (intrinsic_novelty.py:36-40):
+ * zero every slot of each actor b with done_dev[b] != 0; cursor untouched. */
+int ngu_epi_reset(ngu_epi* h, const uint8_t* done_dev, void* stream);
+
+/* Single-shard convenience = scan -> finish (own sums) -> log_update -> append,
+ * i.e. one call of EpisodicNovelty.compute_episodic_novelty followed by the
+ * multiplier of IntrinsicNovelty.compute_intrinsic_novelty
+ * (episodic_novelty.py:37-84, intrinsic_novelty.py:20-34), all on `stream`. */
+int ngu_epi_step(ngu_epi* h, const float* q_dev, const float* alpha_dev,
+                 float* r_int_dev, float* r_epi_dev, void* stream);
+
+/* Same, with HOST buffers (what the Python drop-in calls with CPU tensors):
+ * H2D of q/alpha, the step, D2H of the rewards, synchronous. */
+int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host,
+                      float* r_int_host, float* r_epi_host);
+int ngu_epi_reset_host(ngu_epi* h, const uint8_t* done_host);
+
+/* Last scan's k-NN lists, best first: d2_host float[n_actors][k] (squared
+ * distance, the exact bits of the reference's ((mem-q)**2).sum(-1)),
+ * idx_host int32[n_actors][k] (slot index; ties -> lowest slot).  Synchronous.
+ * The reference discards the indices (episodic_novelty.py:54-56); they are part
+ * of this library's contract. */
+int ngu_epi_topk_host(ngu_epi* h, float* d2_host, int32_t* idx_host);
+
+int ngu_epi_get_state(ngu_epi* h, ngu_epi_state* out);      /* synchronous */
+int ngu_epi_set_state(ngu_epi* h, const ngu_epi_state* in); /* synchronous */
+
+/* Bulk load / dump of the episodic memory in the REFERENCE layout
+ * float[capacity][n_actors][32] on the host (tests, checkpoints).  Synchronous. */
+int ngu_epi_load_memory_host(ngu_epi* h, const float* slot_major_host);
+int ngu_epi_dump_memory_host(ngu_epi* h, float* slot_major_host);
+
+/* Introspection for bench.py / DESIGN.md: kernels launched by the handle so far,
+ * and the scan launch geometry {grid, block, dyn_smem, tiles_per_warp, stages, tile_rows}. */
+int64_t ngu_epi_launch_count(const ngu_epi* h);
+int ngu_epi_scan_geometry(const ngu_epi* h, int32_t out[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGU_EPI_H */

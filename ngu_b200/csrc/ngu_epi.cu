@@ -1,0 +1,515 @@
+// ngu_epi.cu — C ABI (include/ngu_epi.h) over the sm_100a kernels.
+//
+// Host side of the B200 episodic-novelty engine: handle/state management, the
+// TMA tensor map over the episodic memory, launch geometry, and the per-step
+// kernel sequence  scan_topk -> merge_topk -> [exchange] -> finish -> append.
+// No torch headers, no CPU fallback: every entry point needs a CUDA device.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/ngu_epi.h"
+#include "epilogue.cuh"
+#include "scan_topk.cuh"
+
+using namespace ngu;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                             const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+std::string fmt(const char* f, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, f);
+    vsnprintf(buf, sizeof buf, f, ap);
+    va_end(ap);
+    return buf;
+}
+
+// Scan kernel variants (WARPS, STAGES, rows-per-lane); see DESIGN.md "kernel A".
+struct Variant {
+    int warps, stages, rpl, ctas_per_sm;
+    const void* fn;
+    int smem;
+};
+template <int W, int S, int R>
+Variant make_variant(int ctas_per_sm) {
+    return Variant{W, S, R, ctas_per_sm, reinterpret_cast<const void*>(&scan_topk_kernel<W, S, R>),
+                   ScanCfg<W, S, R>::kSmemBytes};
+}
+const Variant kVariants[] = {
+    make_variant<8, 3, 1>(2),   // 0 (default): 16 warps/SM, 3 x 4 KB ring per warp  = 192 KB in flight / SM
+    make_variant<8, 6, 1>(1),   // 1:  8 warps/SM, 6 x 4 KB                         = 192 KB
+    make_variant<8, 3, 2>(1),   // 2:  8 warps/SM, 3 x 8 KB                         = 192 KB
+    make_variant<16, 3, 1>(1),  // 3: 16 warps/SM in one CTA, 3 x 4 KB              = 192 KB
+    make_variant<8, 2, 1>(3),   // 4: 24 warps/SM, 2 x 4 KB                         = 192 KB
+    make_variant<4, 4, 1>(3),   // 5: 12 warps/SM, 4 x 4 KB                         = 192 KB
+    make_variant<8, 4, 1>(1),   // 6:  8 warps/SM, 4 x 4 KB                         = 128 KB
+    make_variant<4, 6, 2>(1),   // 7:  4 warps/SM, 6 x 8 KB                         = 192 KB
+};
+constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+constexpr int kMergeWarps = 8;
+constexpr int kFinishThreads = 512;
+constexpr int kMinTilesPerWarp = 4;
+
+}  // namespace
+
+struct ngu_epi {
+    ngu_epi_cfg cfg{};
+    EpiConsts consts{};
+    int sm_count = 0;
+    bool owns_memory = false;
+    float* memory = nullptr;         // [B][N][32]
+    u64* partial = nullptr;          // [B][max_parts][k]
+    float* topk_d2 = nullptr;        // [B][k]
+    int32_t* topk_idx = nullptr;     // [B][k]
+    float* dist = nullptr;           // [B][k]
+    double* rank_sums = nullptr;     // [2k+1]
+    double* log_sums = nullptr;      // [5]
+    DevState* state = nullptr;
+    // staging for the *_host entry points
+    cudaStream_t own_stream = nullptr;
+    float* q_stage_dev = nullptr;    // [B][32]
+    float* a_stage_dev = nullptr;    // [B]
+    float* r_stage_dev = nullptr;    // [2][B]
+    uint8_t* done_stage_dev = nullptr;
+    float* pinned = nullptr;         // [B*32 + B + 2B] floats + B bytes
+    // launch geometry
+    Variant var{};
+    CUtensorMap tmap{};
+    int grid = 0, tiles_per_actor = 0, tiles_per_warp = 0, max_parts = 0;
+    int64_t total_tiles = 0;
+    bool scanned = false;
+    int64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(ngu_epi* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU_TRY(h, expr)                                                                         \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(h, NGU_ECUDA, fmt("%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+    } while (0)
+
+int bind_device(ngu_epi* h) {
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    return NGU_OK;
+}
+
+int build_tensor_map(ngu_epi* h) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU_TRY(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+        return fail(h, NGU_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+    auto encode = reinterpret_cast<PFN_tensorMapEncodeTiled>(fn);
+    const cuuint64_t rows = static_cast<cuuint64_t>(h->cfg.n_actors) * h->cfg.capacity;
+    const cuuint64_t gdim[2] = {32, rows};
+    const cuuint64_t gstride[1] = {128};   // bytes between rows
+    const cuuint32_t box[2] = {32, static_cast<cuuint32_t>(32 * h->var.rpl)};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&h->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->memory, gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, NGU_ECUDA, fmt("cuTensorMapEncodeTiled failed: CUresult %d", (int)r));
+    return NGU_OK;
+}
+
+void plan_geometry(ngu_epi* h) {
+    const int tile_rows = 32 * h->var.rpl;
+    h->tiles_per_actor = (h->cfg.capacity + tile_rows - 1) / tile_rows;
+    h->total_tiles = static_cast<int64_t>(h->cfg.n_actors) * h->tiles_per_actor;
+    const int64_t max_warps = static_cast<int64_t>(h->sm_count) * h->var.ctas_per_sm * h->var.warps;
+    int64_t tpw = (h->total_tiles + max_warps - 1) / max_warps;
+    if (tpw < kMinTilesPerWarp) tpw = kMinTilesPerWarp;
+    h->tiles_per_warp = static_cast<int>(tpw);
+    const int64_t warps_needed = (h->total_tiles + tpw - 1) / tpw;
+    h->grid = static_cast<int>((warps_needed + h->var.warps - 1) / h->var.warps);
+    h->max_parts = static_cast<int>((h->tiles_per_actor + tpw - 1) / tpw) + 1;
+}
+
+int default_state(ngu_epi* h) {
+    ngu_epi_state s;
+    std::memset(&s, 0, sizeof s);
+    for (int j = 0; j < NGU_EPI_MAX_K; ++j) s.ed_var[j] = 1.0;           // mpi_util.py:39-41
+    s.ed_count = h->cfg.prior_count;                                      // mpi_util.py:42
+    s.epi_var = 1.0;  s.epi_count = 1e-4;                                 // RunningMeanStd() defaults
+    s.intr_var = 1.0; s.intr_count = 1e-4;
+    return ngu_epi_set_state(h, &s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ngu_epi_abi_version(void) { return NGU_EPI_ABI_VERSION; }
+
+const char* ngu_epi_last_error(const ngu_epi* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
+    if (!cfg || !out) return fail(nullptr, NGU_EINVAL, "null cfg/out");
+    *out = nullptr;
+    if (cfg->dim != NGU_EPI_DIM) return fail(nullptr, NGU_EINVAL, fmt("dim must be %d, got %d", NGU_EPI_DIM, cfg->dim));
+    if (cfg->n_actors < 1 || cfg->capacity < 1) return fail(nullptr, NGU_EINVAL, "n_actors and capacity must be >= 1");
+    if (cfg->k < 1 || cfg->k > NGU_EPI_MAX_K) return fail(nullptr, NGU_EINVAL, fmt("k must be in 1..%d, got %d", NGU_EPI_MAX_K, cfg->k));
+    if (cfg->k > cfg->capacity)  // torch.topk raises "selected index k out of range" (episodic_novelty.py:54)
+        return fail(nullptr, NGU_EINVAL, fmt("k=%d exceeds capacity=%d (the reference's topk would raise)", cfg->k, cfg->capacity));
+    if (cfg->mode != NGU_MODE_REFERENCE && cfg->mode != NGU_MODE_PAPER) return fail(nullptr, NGU_EINVAL, "unknown mode");
+    if (static_cast<int64_t>(cfg->n_actors) * cfg->capacity + 256 >= (1ll << 31))
+        return fail(nullptr, NGU_EINVAL, "n_actors*capacity must stay below 2^31 rows per handle; shard the actors");
+    if (cfg->scan_variant < 0 || cfg->scan_variant >= kNumVariants) return fail(nullptr, NGU_EINVAL, "unknown scan_variant");
+    if (memory_dev && (reinterpret_cast<uintptr_t>(memory_dev) & 127u))
+        return fail(nullptr, NGU_EINVAL, "memory_dev must be 128-byte aligned (one row)");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, NGU_ECUDA, fmt("no CUDA device (%s); libngu_epi has no CPU fallback", cudaGetErrorString(e)));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, NGU_EINVAL, "device ordinal out of range");
+
+    ngu_epi* h = new (std::nothrow) ngu_epi();
+    if (!h) return fail(nullptr, NGU_ENOMEM, "host allocation failed");
+    h->cfg = *cfg;
+#define CREATE_TRY(expr)                                                                       \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            g_create_error = fmt("%s: %s", #expr, cudaGetErrorString(e_));                     \
+            ngu_epi_destroy(h);                                                                \
+            return NGU_ECUDA;                                                                  \
+        }                                                                                      \
+    } while (0)
+    CREATE_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CREATE_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) {
+        g_create_error = fmt("device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device, prop.major, prop.minor);
+        ngu_epi_destroy(h);
+        return NGU_EINVAL;
+    }
+    h->sm_count = prop.multiProcessorCount;
+
+    h->var = kVariants[cfg->scan_variant];
+    if (cfg->scan_ctas_per_sm > 0) h->var.ctas_per_sm = cfg->scan_ctas_per_sm;
+    if (static_cast<size_t>(h->var.smem) * h->var.ctas_per_sm > prop.sharedMemPerMultiprocessor ||
+        static_cast<size_t>(h->var.smem) > prop.sharedMemPerBlockOptin) {
+        g_create_error = fmt("scan variant %d needs %d B smem x %d CTAs/SM; device offers %zu", cfg->scan_variant, h->var.smem,
+                             h->var.ctas_per_sm, (size_t)prop.sharedMemPerMultiprocessor);
+        ngu_epi_destroy(h);
+        return NGU_EINVAL;
+    }
+    CREATE_TRY(cudaFuncSetAttribute(h->var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->var.smem));
+    plan_geometry(h);
+
+    const int B = cfg->n_actors, k = cfg->k;
+    const size_t mem_bytes = static_cast<size_t>(B) * cfg->capacity * 32 * sizeof(float);
+    if (memory_dev) {
+        h->memory = memory_dev;
+    } else {
+        CREATE_TRY(cudaMalloc(&h->memory, mem_bytes));
+        h->owns_memory = true;
+        CREATE_TRY(cudaMemset(h->memory, 0, mem_bytes));                 // torch.zeros, episodic_novelty.py:32
+    }
+    CREATE_TRY(cudaMalloc(&h->partial, static_cast<size_t>(B) * h->max_parts * k * sizeof(u64)));
+    CREATE_TRY(cudaMalloc(&h->topk_d2, static_cast<size_t>(B) * k * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&h->topk_idx, static_cast<size_t>(B) * k * sizeof(int32_t)));
+    CREATE_TRY(cudaMalloc(&h->dist, static_cast<size_t>(B) * k * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&h->rank_sums, NGU_EPI_RANK_SUMS(NGU_EPI_MAX_K) * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->log_sums, 8 * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->state, sizeof(DevState)));
+    CREATE_TRY(cudaMemset(h->state, 0, sizeof(DevState)));
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaMalloc(&h->q_stage_dev, static_cast<size_t>(B) * 32 * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&h->a_stage_dev, static_cast<size_t>(B) * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&h->r_stage_dev, static_cast<size_t>(B) * 2 * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&h->done_stage_dev, static_cast<size_t>(B)));
+    CREATE_TRY(cudaMallocHost(&h->pinned, static_cast<size_t>(B) * (32 + 1 + 2) * sizeof(float) + B));
+#undef CREATE_TRY
+
+    EpiConsts& c = h->consts;
+    c.eps = cfg->kernel_epsilon; c.cluster = cfg->cluster_distance; c.pseudo = cfg->pseudo_counts;
+    c.s_max = cfg->max_similarity; c.max_rew = cfg->max_reward_scale;
+    c.k = k; c.n_actors = B; c.capacity = cfg->capacity;
+    c.largest = (cfg->mode == NGU_MODE_REFERENCE) ? 1 : 0;
+    c.sqrt_dist = (cfg->mode == NGU_MODE_REFERENCE) ? 1 : 0;
+
+    int rc = build_tensor_map(h);
+    if (rc == NGU_OK) rc = default_state(h);
+    if (rc != NGU_OK) {
+        g_create_error = h->err;
+        ngu_epi_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return NGU_OK;
+}
+
+void ngu_epi_destroy(ngu_epi* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
+    if (h->owns_memory) cudaFree(h->memory);
+    cudaFree(h->partial); cudaFree(h->topk_d2); cudaFree(h->topk_idx); cudaFree(h->dist);
+    cudaFree(h->rank_sums); cudaFree(h->log_sums); cudaFree(h->state);
+    cudaFree(h->q_stage_dev); cudaFree(h->a_stage_dev); cudaFree(h->r_stage_dev); cudaFree(h->done_stage_dev);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    delete h;
+}
+
+int ngu_epi_memory(ngu_epi* h, float** memory_dev, int64_t strides[3]) {
+    if (!h || !memory_dev || !strides) return fail(h, NGU_EINVAL, "null argument");
+    *memory_dev = h->memory;
+    strides[0] = 32;                                          // slot
+    strides[1] = static_cast<int64_t>(h->cfg.capacity) * 32;  // actor
+    strides[2] = 1;
+    return NGU_OK;
+}
+
+int ngu_epi_scan(ngu_epi* h, const float* q_dev, void* stream) {
+    if (!h || !q_dev) return fail(h, NGU_EINVAL, "null argument");
+    int rc = bind_device(h);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+    ScanParams sp{};
+    sp.q = q_dev; sp.partial = h->partial;
+    sp.n_actors = h->cfg.n_actors; sp.capacity = h->cfg.capacity; sp.k = h->cfg.k;
+    sp.largest = h->consts.largest;
+    sp.tiles_per_actor = h->tiles_per_actor; sp.tiles_per_warp = h->tiles_per_warp;
+    sp.max_parts = h->max_parts; sp.total_tiles = h->total_tiles;
+    void* args[] = {&h->tmap, &sp};
+    CU_TRY(h, cudaLaunchKernel(h->var.fn, dim3(h->grid), dim3(h->var.warps * 32), args, h->var.smem, s));
+
+    MergeParams mp{};
+    mp.partial = h->partial; mp.topk_d2 = h->topk_d2; mp.topk_idx = h->topk_idx; mp.dist = h->dist;
+    mp.rank_sums = h->rank_sums; mp.state = h->state;
+    mp.tiles_per_actor = h->tiles_per_actor; mp.tiles_per_warp = h->tiles_per_warp; mp.max_parts = h->max_parts;
+    const int mgrid = (h->cfg.n_actors + kMergeWarps - 1) / kMergeWarps;
+    merge_topk_kernel<kMergeWarps><<<mgrid, kMergeWarps * 32, 0, s>>>(mp, h->consts);
+    CU_TRY(h, cudaGetLastError());
+    h->launches += 2;
+    h->scanned = true;
+    return NGU_OK;
+}
+
+int ngu_epi_rank_sums(ngu_epi* h, double** sums_dev) {
+    if (!h || !sums_dev) return fail(h, NGU_EINVAL, "null argument");
+    *sums_dev = h->rank_sums;
+    return NGU_OK;
+}
+
+static int finish_impl(ngu_epi* h, const double* sums, const float* alpha, float* r_int, float* r_epi,
+                       double* log_sums, int fuse_log, cudaStream_t s) {
+    if (!h->scanned) return fail(h, NGU_ESTATE, "ngu_epi_finish called before ngu_epi_scan");
+    FinishParams fp{};
+    fp.dist = h->dist; fp.sums = sums ? sums : h->rank_sums; fp.alpha = alpha;
+    fp.r_int = r_int; fp.r_epi = r_epi; fp.log_sums = log_sums; fp.state = h->state;
+    fp.fuse_log_update = fuse_log;
+    finish_kernel<kFinishThreads><<<1, kFinishThreads, 0, s>>>(fp, h->consts);
+    CU_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    h->scanned = false;
+    return NGU_OK;
+}
+
+int ngu_epi_finish(ngu_epi* h, const double* sums_global_dev, const float* alpha_dev, float* r_int_dev,
+                   float* r_epi_dev, double* log_sums_dev, void* stream) {
+    if (!h || !r_int_dev) return fail(h, NGU_EINVAL, "null argument");
+    int rc = bind_device(h);
+    if (rc) return rc;
+    return finish_impl(h, sums_global_dev, alpha_dev, r_int_dev, r_epi_dev, log_sums_dev, 0,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int ngu_epi_log_update(ngu_epi* h, const double* log_sums_global_dev, void* stream) {
+    if (!h || !log_sums_global_dev) return fail(h, NGU_EINVAL, "null argument");
+    int rc = bind_device(h);
+    if (rc) return rc;
+    log_update_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(h->state, log_sums_global_dev);
+    CU_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return NGU_OK;
+}
+
+int ngu_epi_append(ngu_epi* h, const float* q_dev, void* stream) {
+    if (!h || !q_dev) return fail(h, NGU_EINVAL, "null argument");
+    int rc = bind_device(h);
+    if (rc) return rc;
+    append_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(h->memory, q_dev, h->state, h->cfg.n_actors,
+                                                                    h->cfg.capacity);
+    CU_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return NGU_OK;
+}
+
+int ngu_epi_reset(ngu_epi* h, const uint8_t* done_dev, void* stream) {
+    if (!h || !done_dev) return fail(h, NGU_EINVAL, "null argument");
+    int rc = bind_device(h);
+    if (rc) return rc;
+    const int64_t n4 = static_cast<int64_t>(h->cfg.capacity) * 8;
+    dim3 grid(static_cast<unsigned>((n4 + 2047) / 2048), h->cfg.n_actors);
+    reset_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->memory, done_dev, h->cfg.capacity);
+    CU_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return NGU_OK;
+}
+
+int ngu_epi_step(ngu_epi* h, const float* q_dev, const float* alpha_dev, float* r_int_dev, float* r_epi_dev,
+                 void* stream) {
+    if (!h || !q_dev || !r_int_dev) return fail(h, NGU_EINVAL, "null argument");
+    int rc = ngu_epi_scan(h, q_dev, stream);
+    if (rc) return rc;
+    rc = finish_impl(h, nullptr, alpha_dev, r_int_dev, r_epi_dev, nullptr, 1, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+    return ngu_epi_append(h, q_dev, stream);
+}
+
+int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host, float* r_int_host,
+                      float* r_epi_host) {
+    if (!h || !q_host || !r_int_host) return fail(h, NGU_EINVAL, "null argument");
+    int rc = bind_device(h);
+    if (rc) return rc;
+    const int B = h->cfg.n_actors;
+    cudaStream_t s = h->own_stream;
+    float* pq = h->pinned;
+    float* pa = pq + static_cast<size_t>(B) * 32;
+    float* pr = pa + B;
+    std::memcpy(pq, q_host, static_cast<size_t>(B) * 32 * sizeof(float));
+    CU_TRY(h, cudaMemcpyAsync(h->q_stage_dev, pq, static_cast<size_t>(B) * 32 * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (alpha_host) {
+        std::memcpy(pa, alpha_host, static_cast<size_t>(B) * sizeof(float));
+        CU_TRY(h, cudaMemcpyAsync(h->a_stage_dev, pa, static_cast<size_t>(B) * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    rc = ngu_epi_step(h, h->q_stage_dev, alpha_host ? h->a_stage_dev : nullptr, h->r_stage_dev, h->r_stage_dev + B, s);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(pr, h->r_stage_dev, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaStreamSynchronize(s));
+    std::memcpy(r_int_host, pr, static_cast<size_t>(B) * sizeof(float));
+    if (r_epi_host) std::memcpy(r_epi_host, pr + B, static_cast<size_t>(B) * sizeof(float));
+    return NGU_OK;
+}
+
+int ngu_epi_reset_host(ngu_epi* h, const uint8_t* done_host) {
+    if (!h || !done_host) return fail(h, NGU_EINVAL, "null argument");
+    int rc = bind_device(h);
+    if (rc) return rc;
+    const int B = h->cfg.n_actors;
+    bool any = false;
+    for (int b = 0; b < B; ++b) any |= done_host[b] != 0;
+    if (!any) return NGU_OK;   // nothing to zero: skip the launch (the common step)
+    uint8_t* pd = reinterpret_cast<uint8_t*>(h->pinned + static_cast<size_t>(B) * 35);
+    std::memcpy(pd, done_host, B);
+    CU_TRY(h, cudaMemcpyAsync(h->done_stage_dev, pd, B, cudaMemcpyHostToDevice, h->own_stream));
+    rc = ngu_epi_reset(h, h->done_stage_dev, h->own_stream);
+    if (rc) return rc;
+    CU_TRY(h, cudaStreamSynchronize(h->own_stream));
+    return NGU_OK;
+}
+
+int ngu_epi_topk_host(ngu_epi* h, float* d2_host, int32_t* idx_host) {
+    if (!h || !d2_host || !idx_host) return fail(h, NGU_EINVAL, "null argument");
+    int rc = bind_device(h);
+    if (rc) return rc;
+    CU_TRY(h, cudaDeviceSynchronize());
+    const size_t n = static_cast<size_t>(h->cfg.n_actors) * h->cfg.k;
+    CU_TRY(h, cudaMemcpy(d2_host, h->topk_d2, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CU_TRY(h, cudaMemcpy(idx_host, h->topk_idx, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return NGU_OK;
+}
+
+int ngu_epi_get_state(ngu_epi* h, ngu_epi_state* out) {
+    if (!h || !out) return fail(h, NGU_EINVAL, "null argument");
+    int rc = bind_device(h);
+    if (rc) return rc;
+    DevState d;
+    CU_TRY(h, cudaDeviceSynchronize());
+    CU_TRY(h, cudaMemcpy(&d, h->state, sizeof d, cudaMemcpyDeviceToHost));
+    std::memcpy(out->ed_mean, d.ed_mean, sizeof d.ed_mean);
+    std::memcpy(out->ed_var, d.ed_var, sizeof d.ed_var);
+    out->ed_count = d.ed_count;
+    out->epi_mean = d.epi_mean; out->epi_var = d.epi_var; out->epi_count = d.epi_count;
+    out->intr_mean = d.intr_mean; out->intr_var = d.intr_var; out->intr_count = d.intr_count;
+    out->cursor = d.cursor; out->steps = d.steps;
+    return NGU_OK;
+}
+
+int ngu_epi_set_state(ngu_epi* h, const ngu_epi_state* in) {
+    if (!h || !in) return fail(h, NGU_EINVAL, "null argument");
+    if (in->cursor < 0 || in->cursor >= h->cfg.capacity) return fail(h, NGU_EINVAL, "cursor out of range");
+    int rc = bind_device(h);
+    if (rc) return rc;
+    DevState d;
+    std::memset(&d, 0, sizeof d);
+    std::memcpy(d.ed_mean, in->ed_mean, sizeof d.ed_mean);
+    std::memcpy(d.ed_var, in->ed_var, sizeof d.ed_var);
+    d.ed_count = in->ed_count;
+    d.epi_mean = in->epi_mean; d.epi_var = in->epi_var; d.epi_count = in->epi_count;
+    d.intr_mean = in->intr_mean; d.intr_var = in->intr_var; d.intr_count = in->intr_count;
+    d.cursor = in->cursor; d.steps = in->steps;
+    CU_TRY(h, cudaDeviceSynchronize());
+    CU_TRY(h, cudaMemcpy(h->state, &d, sizeof d, cudaMemcpyHostToDevice));
+    return NGU_OK;
+}
+
+static int transpose_copy(ngu_epi* h, const float* host_in, float* host_out) {
+    int rc = bind_device(h);
+    if (rc) return rc;
+    const int B = h->cfg.n_actors, N = h->cfg.capacity;
+    const size_t bytes = static_cast<size_t>(B) * N * 32 * sizeof(float);
+    float* tmp = nullptr;
+    CU_TRY(h, cudaDeviceSynchronize());
+    CU_TRY(h, cudaMalloc(&tmp, bytes));
+    cudaError_t e = cudaSuccess;
+    if (host_in) {   // [N][B][32] host -> [B][N][32] device
+        e = cudaMemcpy(tmp, host_in, bytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            transpose_rows_kernel<<<1024, 256>>>(reinterpret_cast<float4*>(h->memory), reinterpret_cast<const float4*>(tmp), N, B);
+            e = cudaDeviceSynchronize();
+        }
+    } else {         // [B][N][32] device -> [N][B][32] host
+        transpose_rows_kernel<<<1024, 256>>>(reinterpret_cast<float4*>(tmp), reinterpret_cast<const float4*>(h->memory), B, N);
+        e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaMemcpy(host_out, tmp, bytes, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(tmp);
+    h->launches += 1;
+    if (e != cudaSuccess) return fail(h, NGU_ECUDA, fmt("memory load/dump: %s", cudaGetErrorString(e)));
+    return NGU_OK;
+}
+
+int ngu_epi_load_memory_host(ngu_epi* h, const float* slot_major_host) {
+    if (!h || !slot_major_host) return fail(h, NGU_EINVAL, "null argument");
+    return transpose_copy(h, slot_major_host, nullptr);
+}
+int ngu_epi_dump_memory_host(ngu_epi* h, float* slot_major_host) {
+    if (!h || !slot_major_host) return fail(h, NGU_EINVAL, "null argument");
+    return transpose_copy(h, nullptr, slot_major_host);
+}
+
+int64_t ngu_epi_launch_count(const ngu_epi* h) { return h ? h->launches : 0; }
+
+int ngu_epi_scan_geometry(const ngu_epi* h, int32_t out[6]) {
+    if (!h || !out) return NGU_EINVAL;
+    out[0] = h->grid; out[1] = h->var.warps * 32; out[2] = h->var.smem;
+    out[3] = h->tiles_per_warp; out[4] = h->var.stages; out[5] = 32 * h->var.rpl;
+    return NGU_OK;
+}
+
+}  // extern "C"

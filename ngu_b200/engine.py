@@ -1,0 +1,211 @@
+"""EpisodicEngine — thin Python owner of one libngu_epi handle (one GPU, one shard of actors).
+
+PyTorch is plumbing here: it owns the device buffers (so the episodic memory is
+a normal ``torch.Tensor`` the caller can read, exactly like the reference's
+``EpisodicNovelty.episodic_memory``) and provides the CUDA stream; all compute
+is in the sm_100a kernels behind the C ABI (include/ngu_epi.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import NguEpiCfg, NguEpiState, check
+
+# model_hypr keys read by the reference (ngu/models/model_hypr.py:52-57)
+DEFAULT_HYPR = dict(
+    episodic_memory_capacity=30000,
+    kernel_epsilon=0.0001,
+    num_neighbors=10,
+    cluster_distance=0.008,
+    kernel_pseudo_counts_constant=0.001,
+    kernel_maximum_similarity=8,
+)
+
+
+class _DevArray:
+    """Zero-copy view of a raw device pointer for torch.as_tensor."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {
+            "data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 2}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class EpisodicEngine:
+    """One actor shard on one B200.
+
+    Args mirror ``EpisodicNovelty.__init__`` (episodic_novelty.py:9-35) after
+    the hyper-parameter dict has been unpacked.  ``prior_count=None`` reproduces
+    the reference's ``RunningMeanStd((k,))`` quirk (count starts at k).
+    """
+
+    def __init__(self, n_actors, capacity, k=10, kernel_epsilon=1e-4, cluster_distance=0.008,
+                 pseudo_counts=1e-3, max_similarity=8.0, max_reward_scale=5.0, mode="reference",
+                 device=None, prior_count=None, scan_variant=0, scan_ctas_per_sm=0):
+        self._lib = _cabi.load()
+        if not torch.cuda.is_available():
+            raise _cabi.NguEpiError("ngu_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.n_actors, self.capacity, self.k = int(n_actors), int(capacity), int(k)
+        self.mode = mode
+        cfg = NguEpiCfg(
+            n_actors=self.n_actors, capacity=self.capacity, dim=_cabi.DIM, k=self.k,
+            mode={"reference": _cabi.MODE_REFERENCE, "paper": _cabi.MODE_PAPER}[mode],
+            device=self.device.index,
+            kernel_epsilon=kernel_epsilon, cluster_distance=cluster_distance, pseudo_counts=pseudo_counts,
+            max_similarity=max_similarity, max_reward_scale=max_reward_scale, reserved0=0.0,
+            prior_count=float(self.k if prior_count is None else prior_count),
+            scan_ctas_per_sm=scan_ctas_per_sm, scan_variant=scan_variant)
+        # torch owns the episodic memory: actor-major [B][N][32], zero-initialised
+        self._memory = torch.zeros((self.n_actors, self.capacity, _cabi.DIM), dtype=torch.float32, device=self.device)
+        h = C.c_void_p()
+        rc = self._lib.ngu_epi_create(C.byref(cfg), _ptr(self._memory), C.byref(h))
+        check(rc, None)
+        self._h = h
+        p = C.c_void_p()
+        check(self._lib.ngu_epi_rank_sums(self._h, C.byref(p)), self._h)
+        self.rank_sums = torch.as_tensor(_DevArray(p.value, (2 * self.k + 1,), "<f8"), device=self.device)
+        self._r_int = torch.empty(self.n_actors, dtype=torch.float32, device=self.device)
+        self._r_epi = torch.empty(self.n_actors, dtype=torch.float32, device=self.device)
+        self.log_sums = torch.zeros(5, dtype=torch.float64, device=self.device)
+
+    # ---- lifetime -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ngu_epi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- views ----------------------------------------------------------------
+    @property
+    def episodic_memory(self) -> torch.Tensor:
+        """(capacity, n_actors, 32) strided view, the reference's layout (episodic_novelty.py:32-33)."""
+        return self._memory.permute(1, 0, 2)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _q(self, q: torch.Tensor) -> torch.Tensor:
+        if q.device != self.device or q.dtype != torch.float32 or not q.is_contiguous():
+            q = q.to(device=self.device, dtype=torch.float32).contiguous()
+        if tuple(q.shape) != (self.n_actors, _cabi.DIM):
+            raise ValueError(f"controllable state must be ({self.n_actors}, {_cabi.DIM}), got {tuple(q.shape)}")
+        return q
+
+    # ---- device-pointer path (no host sync) -------------------------------------
+    def scan(self, q: torch.Tensor):
+        self._q_keep = self._q(q)
+        check(self._lib.ngu_epi_scan(self._h, _ptr(self._q_keep), self._stream()), self._h)
+
+    def finish(self, sums_global=None, alpha=None, want_log_sums=False):
+        if alpha is not None:
+            alpha = alpha.to(device=self.device, dtype=torch.float32).contiguous()
+        self._alpha_keep = alpha
+        check(self._lib.ngu_epi_finish(self._h, _ptr(sums_global), _ptr(alpha), _ptr(self._r_int), _ptr(self._r_epi),
+                                       _ptr(self.log_sums) if want_log_sums else None, self._stream()), self._h)
+        return self._r_int, self._r_epi
+
+    def log_update(self, log_sums_global: torch.Tensor):
+        check(self._lib.ngu_epi_log_update(self._h, _ptr(log_sums_global), self._stream()), self._h)
+
+    def append(self, q: torch.Tensor):
+        self._q_keep = self._q(q)
+        check(self._lib.ngu_epi_append(self._h, _ptr(self._q_keep), self._stream()), self._h)
+
+    def reset(self, done: torch.Tensor):
+        done = done.to(device=self.device).to(torch.uint8).contiguous()
+        self._done_keep = done
+        check(self._lib.ngu_epi_reset(self._h, _ptr(done), self._stream()), self._h)
+
+    def step(self, q: torch.Tensor, alpha: torch.Tensor | None = None):
+        """scan -> finish -> append on the current stream; returns device tensors (r_int, r_epi)."""
+        self._q_keep = self._q(q)
+        if alpha is not None:
+            alpha = alpha.to(device=self.device, dtype=torch.float32).contiguous()
+        self._alpha_keep = alpha
+        check(self._lib.ngu_epi_step(self._h, _ptr(self._q_keep), _ptr(alpha), _ptr(self._r_int), _ptr(self._r_epi),
+                                     self._stream()), self._h)
+        return self._r_int, self._r_epi
+
+    # ---- host-buffer path (what the drop-in calls with CPU tensors) ---------------
+    def step_host(self, q: np.ndarray, alpha: np.ndarray | None = None):
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        if q.shape != (self.n_actors, _cabi.DIM):
+            raise ValueError(f"controllable state must be ({self.n_actors}, {_cabi.DIM}), got {q.shape}")
+        a = None if alpha is None else np.ascontiguousarray(alpha, dtype=np.float32)
+        r_int = np.empty(self.n_actors, np.float32)
+        r_epi = np.empty(self.n_actors, np.float32)
+        check(self._lib.ngu_epi_step_host(self._h, q.ctypes.data_as(C.c_void_p),
+                                          None if a is None else a.ctypes.data_as(C.c_void_p),
+                                          r_int.ctypes.data_as(C.c_void_p), r_epi.ctypes.data_as(C.c_void_p)), self._h)
+        return r_int, r_epi
+
+    def reset_host(self, done: np.ndarray):
+        d = np.ascontiguousarray(done, dtype=np.uint8)
+        if d.shape != (self.n_actors,):
+            raise ValueError(f"done must be ({self.n_actors},), got {d.shape}")
+        check(self._lib.ngu_epi_reset_host(self._h, d.ctypes.data_as(C.c_void_p)), self._h)
+
+    # ---- results / state ------------------------------------------------------------
+    def topk(self):
+        """Last scan's (d2 [B,k] f32, idx [B,k] i32), best first."""
+        d2 = np.empty((self.n_actors, self.k), np.float32)
+        idx = np.empty((self.n_actors, self.k), np.int32)
+        check(self._lib.ngu_epi_topk_host(self._h, d2.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p)), self._h)
+        return d2, idx
+
+    def get_state(self) -> dict:
+        s = NguEpiState()
+        check(self._lib.ngu_epi_get_state(self._h, C.byref(s)), self._h)
+        k = self.k
+        return dict(ed_mean=np.array(s.ed_mean[:k]), ed_var=np.array(s.ed_var[:k]), ed_count=s.ed_count,
+                    epi_mean=s.epi_mean, epi_var=s.epi_var, epi_count=s.epi_count,
+                    intr_mean=s.intr_mean, intr_var=s.intr_var, intr_count=s.intr_count,
+                    cursor=int(s.cursor), steps=int(s.steps))
+
+    def set_state(self, st: dict):
+        s = NguEpiState()
+        check(self._lib.ngu_epi_get_state(self._h, C.byref(s)), self._h)
+        for j in range(self.k):
+            if "ed_mean" in st: s.ed_mean[j] = float(np.ravel(st["ed_mean"])[j])
+            if "ed_var" in st: s.ed_var[j] = float(np.ravel(st["ed_var"])[j])
+        for name in ("ed_count", "epi_mean", "epi_var", "epi_count", "intr_mean", "intr_var", "intr_count"):
+            if name in st: setattr(s, name, float(st[name]))
+        for name in ("cursor", "steps"):
+            if name in st: setattr(s, name, int(st[name]))
+        check(self._lib.ngu_epi_set_state(self._h, C.byref(s)), self._h)
+
+    def load_memory(self, slot_major: np.ndarray):
+        """Load a host array in the reference layout (capacity, n_actors, 32)."""
+        m = np.ascontiguousarray(slot_major, dtype=np.float32)
+        if m.shape != (self.capacity, self.n_actors, _cabi.DIM):
+            raise ValueError(f"expected {(self.capacity, self.n_actors, _cabi.DIM)}, got {m.shape}")
+        check(self._lib.ngu_epi_load_memory_host(self._h, m.ctypes.data_as(C.c_void_p)), self._h)
+
+    def dump_memory(self) -> np.ndarray:
+        out = np.empty((self.capacity, self.n_actors, _cabi.DIM), np.float32)
+        check(self._lib.ngu_epi_dump_memory_host(self._h, out.ctypes.data_as(C.c_void_p)), self._h)
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.ngu_epi_launch_count(self._h))
+
+    def scan_geometry(self) -> dict:
+        g = (C.c_int32 * 6)()
+        check(self._lib.ngu_epi_scan_geometry(self._h, g), self._h)
+        return dict(grid=g[0], block=g[1], dyn_smem=g[2], tiles_per_warp=g[3], stages=g[4], tile_rows=g[5])

@@ -1,0 +1,177 @@
+#!/usr/bin/env python
+"""Generate golden trajectories by executing the UNMODIFIED reference module.
+
+Runs only in the build container (needs ``/root/reference``); the fixtures it
+writes (``tests/golden/*.npz``) are committed and are what travels to the GPU
+box.  The reference (minoring/NGU) has no tests or golden vectors of its own
+(SURVEY.md section 4), so these files are the pin for both the oracle and the
+CUDA path.
+
+How the reference is driven:
+  * ``mpi4py`` is absent here; a single-rank stand-in whose
+    ``COMM_WORLD.Allreduce(send, recv, op)`` copies ``send`` into ``recv`` is
+    put on ``sys.path`` first (exactly one-rank MPI semantics for
+    ``ngu/utils/mpi_util.py:17``).
+  * ``IntrinsicNovelty`` is constructed unmodified; its CNN producers are
+    bypassed by ``epi_novel.embedding = identity`` (so ``obs`` is the (B,32)
+    controllable state) and by injecting a known RND modulator ``alpha`` through
+    ``ll_novel.compute_lifelong_curiosity``.
+  * Recorded per step: reference rewards (f64 under numpy>=2), the values of the
+    reference's own ``topk`` on d^2, canonical indices (stable descending sort of
+    the reference's distance expression; torch's own tie order is unspecified),
+    and the ``ed_rms`` state.
+
+Usage:  python tests/golden/make_golden.py        (writes next to this file)
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("NGU_REFERENCE", "/root/reference")
+
+SHIM = '''
+class _Comm:
+    def Allreduce(self, send, recv, op=None):
+        recv[...] = send
+class MPI:
+    SUM = "sum"
+    COMM_WORLD = _Comm()
+'''
+
+
+def _import_reference():
+    shim_dir = tempfile.mkdtemp(prefix="mpi4py_shim_")
+    os.makedirs(os.path.join(shim_dir, "mpi4py"))
+    with open(os.path.join(shim_dir, "mpi4py", "__init__.py"), "w") as f:
+        f.write(SHIM)
+    sys.path[:0] = [shim_dir, REF]
+    import torch
+    import ngu.utils.pytorch_util as ptu
+    ptu.init_device(use_gpu=False)
+    from ngu.models.intrinsic_novelty import IntrinsicNovelty
+    from ngu.models.model_hypr import model_hypr
+    return torch, IntrinsicNovelty, model_hypr
+
+
+class _NullLogger:
+    def log_scalar(self, *a, **k):
+        pass
+
+
+# name, B, N, steps, seed, scale, p_done, prefill ("none"|"randn"|"half_zero"|"dups"), alpha ("ones"|"randn")
+CASES = [
+    ("first_steps_zero_memory", 4, 64, 12, 11, 1.0, 0.0, "none", "ones"),
+    ("ring_wrap_n64",           3, 64, 200, 12, 1.0, 0.0, "none", "randn"),
+    ("resets_mid_trajectory",   7, 50, 120, 13, 1.0, 0.05, "none", "randn"),
+    ("single_actor",            1, 777, 40, 14, 1.0, 0.02, "randn", "randn"),
+    ("n_equals_k",              5, 10, 30, 15, 1.0, 0.0, "randn", "ones"),
+    ("half_zero_slots",         6, 500, 25, 16, 1.0, 0.0, "half_zero", "randn"),
+    ("duplicates_across_rank_k", 4, 96, 25, 17, 1.0, 0.0, "dups", "ones"),
+    ("scale_1e-3",              5, 300, 25, 18, 1e-3, 0.0, "randn", "randn"),
+    ("scale_50",                5, 300, 25, 19, 50.0, 0.0, "randn", "randn"),
+    ("b64_n5000",              64, 5000, 6, 20, 1.0, 0.0, "randn", "randn"),
+    ("b256_n300",             256, 300, 8, 21, 1.0, 0.01, "randn", "randn"),
+]
+
+
+def prefill_memory(prefill, N, B, seed, scale):
+    """Initial episodic memory [N,B,32] f32 from numpy's PCG64 stream (platform
+    independent, unlike torch's vectorised CPU normal_), so tests can rebuild
+    the large prefills from (recipe, seed) instead of storing them."""
+    if prefill == "none":
+        return None
+    rng = np.random.default_rng(seed + 1000)
+    if prefill == "randn":
+        return (rng.standard_normal((N, B, 32), dtype=np.float32) * np.float32(scale))
+    if prefill == "half_zero":
+        m = rng.standard_normal((N, B, 32), dtype=np.float32) * np.float32(scale)
+        m[rng.random(N) < 0.5] = 0.0
+        return m
+    if prefill == "dups":
+        # few distinct rows repeated many times: exact d^2 ties straddle rank k
+        base = rng.standard_normal((6, B, 32), dtype=np.float32) * np.float32(scale)
+        return base[rng.integers(0, 6, size=N)].copy()
+    raise ValueError(prefill)
+
+
+def run_case(torch, IntrinsicNovelty, model_hypr, name, B, N, steps, seed, scale, p_done, prefill, alpha_kind):
+    hy = dict(model_hypr, episodic_memory_capacity=N)
+    inn = IntrinsicNovelty(B, 18, (1, 84, 84), hy, _NullLogger())
+    en = inn.epi_novel
+    en.embedding = lambda x: x
+    g = torch.Generator().manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    k = hy["num_neighbors"]
+
+    mem_init = prefill_memory(prefill, N, B, seed, scale)
+    if mem_init is not None:
+        en.episodic_memory = torch.from_numpy(mem_init.copy())
+    mem0 = en.episodic_memory.numpy().copy()
+
+    rec = {k_: [] for k_ in ("q", "alpha", "done", "reward", "d2", "idx", "mean", "var", "count")}
+    for _ in range(steps):
+        q = torch.randn(B, 32, generator=g) * scale
+        alpha = np.ones(B) if alpha_kind == "ones" else 1.0 + 2.0 * rng.standard_normal(B)
+        inn.ll_novel.compute_lifelong_curiosity = lambda obs, a=alpha: torch.from_numpy(a.copy())
+        # the reference's own distance expression, episodic_novelty.py:51-52 (pre-sqrt)
+        d2_all = ((en.episodic_memory - q.unsqueeze(0)) ** 2).sum(dim=-1)
+        ref_topk = d2_all.topk(k, dim=0)                       # values only are well defined
+        canon = torch.sort(d2_all, dim=0, descending=True, stable=True)
+        assert torch.equal(canon.values[:k], ref_topk.values)
+        out = inn.compute_intrinsic_novelty(q)                 # THE reference call
+        done = rng.random(B) < p_done
+        inn.reset_memory_if_done(torch.from_numpy(done))
+        rec["q"].append(q.numpy().copy())
+        rec["alpha"].append(alpha.copy())
+        rec["done"].append(done.copy())
+        rec["reward"].append(out.numpy()[:, 0].astype(np.float64))
+        rec["d2"].append(ref_topk.values.numpy().copy())
+        rec["idx"].append(canon.indices[:k].numpy().astype(np.int32))
+        rec["mean"].append(np.broadcast_to(en.ed_rms.mean, (k,)).astype(np.float64).copy())
+        rec["var"].append(np.broadcast_to(np.ravel(en.ed_rms.var), (k,)).astype(np.float64).copy())
+        rec["count"].append(float(np.ravel(en.ed_rms.count)[0]))
+    out = {k_: np.stack(v) for k_, v in rec.items()}
+    out["mem0"] = mem0
+    out["mem_final"] = en.episodic_memory.numpy().copy()
+    out["cursor_final"] = np.int64(en.memory_idx)
+    out["meta"] = np.array([B, N, k, steps, seed], dtype=np.int64)
+    out["scale"] = np.float64(scale)
+    out["prefill"] = np.array([prefill])
+    out["versions"] = np.array([f"torch {torch.__version__}", f"numpy {np.__version__}"])
+    # big prefilled memories are regenerated from the seed by the tests, not stored
+    if mem0.nbytes > (1 << 20):
+        out["mem0"] = np.zeros((0,), np.float32)
+        out["mem_final"] = np.zeros((0,), np.float32)
+        out["mem_final_sum"] = np.float64(en.episodic_memory.double().sum().item())
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+    print(f"{name}: B={B} N={N} steps={steps} reward[0,:3]={out['reward'][0, :3]}")
+
+
+def lane8_probe(torch):
+    """torch CPU's D=32 sum order must be the lane-8 order
+    on the machine that produced the goldens."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle.episodic_oracle import d2_lane8
+    g = torch.Generator().manual_seed(99)
+    mem = torch.randn(20000, 8, 32, generator=g)
+    q = torch.randn(8, 32, generator=g)
+    ref = ((mem - q.unsqueeze(0)) ** 2).sum(dim=-1).numpy()
+    mine = d2_lane8(mem.numpy(), q.numpy()[None])
+    frac = float((ref.view(np.uint32) == mine.view(np.uint32)).mean())
+    print("lane-8 bit match vs torch CPU:", frac)
+    assert frac == 1.0
+    return frac
+
+
+def main():
+    torch, IntrinsicNovelty, model_hypr = _import_reference()
+    lane8_probe(torch)
+    for case in CASES:
+        run_case(torch, IntrinsicNovelty, model_hypr, *case)
+
+
+if __name__ == "__main__":
+    main()
