@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — episodic intrinsic-reward queries/sec on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              # this repo's CUDA path
+    python bench.py --impl reference [--gpus N --steps K --warmup W] # the reference's CPU path (torch port)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...            # one rank per GPU
+
+A step = one pass of the hot path over one batch of synthetic controllable
+states: distance scan of every actor's whole memory + top-k(10) + running-mean
+update + reward epilogue (x RND multiplier clipped to [1,5]) + append.
+Workload (BASELINE.json configs[2]): 256 actors x 30 000-slot memory x D=32 per
+GPU, memory fully populated with N(0,1) rows (983 MB per GPU, 7.8x the 126 MB
+L2, so every step streams from HBM).  Multi-GPU: actors are sharded, 256 per
+GPU (weak scaling); the only exchange is the 21-double rank-sum all-reduce.
+
+One JSON line on stdout (rank 0).  `value` = whole-job queries/s with inputs
+resident in HBM; `e2e` = the same through the host-buffer C-ABI call
+(ngu_epi_step_host: pinned H2D of the step's states + modulators, D2H of the
+rewards, synchronous).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ACTORS_PER_GPU = 256
+CAPACITY = 30000
+K_NEIGHBORS = 10
+METRIC = "episodic intrinsic-reward queries/sec"
+UNIT = "queries/s"
+BYTES_PER_QUERY = 128 * CAPACITY + 340          # memory read + query + append + outputs
+
+
+def workload_name(actors, capacity):
+    return f"synthetic episodic kNN: {actors} actors/GPU x {capacity // 1000}k-slot memory x D=32, k={K_NEIGHBORS}"
+
+
+# ---------------------------------------------------------------------------------
+# clocks (NVML, sampled from a thread while the timed region runs)
+# ---------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.ok = [], set(), False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max = None
+
+    def _one(self):
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self._one()
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.ok:
+            self._one()
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        if self.ok:
+            self._one()
+            self._stop.set()
+            self.t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------
+# CPU arm: the reference's op sequence on torch CPU (oracle/torch_port.py)
+# ---------------------------------------------------------------------------------
+def cpu_reference_run(actors, capacity, steps, warmup, time_budget_s=None):
+    """Times the torch-CPU port of the reference on `actors` x `capacity`; returns (q/s, ms/step, steps timed, threads)."""
+    import torch
+    from oracle.torch_port import TorchCpuPort
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    port = TorchCpuPort(actors, capacity, k=K_NEIGHBORS)
+    g = torch.Generator().manual_seed(1234)
+    port.memory = torch.randn(capacity, actors, 32, generator=g)
+    qs = [torch.randn(actors, 32, generator=g) for _ in range(4)]
+    al = [(1.0 + torch.randn(actors, generator=g)).double().numpy() for _ in range(4)]
+    for i in range(warmup):
+        port.step(qs[i % 4], al[i % 4])
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(steps):
+        port.step(qs[i % 4], al[i % 4])
+        done += 1
+        if time_budget_s is not None and done >= 3 and time.perf_counter() - t0 > time_budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return actors * done / dt, dt / done * 1e3, done, torch.get_num_threads()
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    # each step is a bounded sample of the workload: the same 256 x 30k shape on the host
+    steps = min(args.steps, 40)
+    qps, ms, done, threads = cpu_reference_run(ACTORS_PER_GPU, CAPACITY, steps, min(args.warmup, 3), time_budget_s=120)
+    sample = (f"{done} steps of {ACTORS_PER_GPU} actors x {CAPACITY} slots on torch-CPU, op-for-op port of the "
+              f"reference (oracle/torch_port.py), {threads} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": done, "warmup": min(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(ACTORS_PER_GPU, CAPACITY), "actors_per_gpu": ACTORS_PER_GPU,
+                   "capacity": CAPACITY, "k": K_NEIGHBORS, "device": "host CPU"},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    return None
+
+
+def run_gpu_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from ngu_b200.sharding import ShardedEpisodicEngine
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, N = args.actors_per_gpu, args.capacity
+    sh = ShardedEpisodicEngine(B * world, N, device=local_rank, k=K_NEIGHBORS,
+                               scan_variant=args.scan_variant, track_log_stats=True)
+    eng = sh.engine
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    eng._memory.normal_(generator=g)                    # fully populated memory
+    NQ = 8
+    qs = [torch.randn(B, 32, device=dev, generator=g) for _ in range(NQ)]
+    al = [1.0 + torch.randn(B, device=dev, generator=g) for _ in range(NQ)]
+    q_host = [q.cpu().pin_memory() for q in qs]
+    a_host = [a.cpu().pin_memory() for a in al]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up: W steps, then keep stepping (untimed) until the clocks have had time to ramp
+    for i in range(args.warmup):
+        sh.step(qs[i % NQ], al[i % NQ])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    i = 0
+    while time.perf_counter() - t0 < 0.25:
+        sh.step(qs[i % NQ], al[i % NQ]); i += 1
+        if i % 64 == 0:
+            torch.cuda.synchronize()
+    barrier()
+
+    # ---- timed region: K steps, device-resident inputs, CUDA events on the launching stream ----
+    K = args.steps
+    launches0 = eng.launch_count
+    eng.scan_timing_begin(K)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record()
+        for i in range(K):
+            sh.step(qs[i % NQ], al[i % NQ])
+        ev1.record()
+        barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    scan_ms, scan_calls = eng.scan_timing_end()
+    launches = eng.launch_count - launches0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = B * world * K / (ms_total / 1e3)
+
+    # ---- e2e: host buffers through the C ABI (pinned H2D + step + D2H, synchronous) ----
+    def e2e_step(i):
+        if world == 1:
+            return eng.step_host(q_host[i % NQ].numpy(), a_host[i % NQ].numpy())[0]
+        q = q_host[i % NQ].to(dev, non_blocking=True)
+        a = a_host[i % NQ].to(dev, non_blocking=True)
+        return sh.step(q, a)[0].cpu()
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * K / float(t.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        scan_avg_ms = scan_ms / max(scan_calls, 1)
+        achieved = BYTES_PER_QUERY_FOR(N) * B / (scan_avg_ms / 1e3) / 1e9
+        geo = eng.scan_geometry()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(B, N), "actors_per_gpu": B, "global_actors": B * world,
+                       "capacity": N, "k": K_NEIGHBORS, "mode": "reference", "parallelism": f"actor-shard x{world}",
+                       "l2": f"working set {B * N * 128 / 1e6:.0f} MB per GPU vs 126 MB L2 (inputs larger than L2)"
+                             if B * N * 128 > 2 * 126e6 else "working set fits L2: cache-resident, flagged",
+                       "exchange": "none" if world == 1 else "21-double rank-sum all-reduce (NCCL) per step",
+                       "scan_geometry": geo},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 32 * 4 + B * 4,
+                    "d2h_bytes_per_step": 2 * B * 4 if world == 1 else B * 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                         "peak_source": peak_src, "launch_ms": scan_avg_ms,
+                         "algorithmic_bytes_per_launch": BYTES_PER_QUERY_FOR(N) * B},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            qps, ms, done, threads = cpu_reference_run(B, N, 30, 1, time_budget_s=12)
+            line["cpu_baseline"] = {
+                "value": qps, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"{done} steps of the same {B} x {N} workload, torch-CPU op-for-op port of the reference "
+                          f"(oracle/torch_port.py), {ms:.1f} ms/step"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def BYTES_PER_QUERY_FOR(capacity):
+    return 128 * capacity + 340
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--actors-per-gpu", type=int, default=ACTORS_PER_GPU)
+    ap.add_argument("--capacity", type=int, default=CAPACITY)
+    ap.add_argument("--scan-variant", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run, one rank per GPU
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

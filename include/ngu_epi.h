@@ -181,6 +181,13 @@ int ngu_epi_dump_memory_host(ngu_epi* h, float* slot_major_host);
 int64_t ngu_epi_launch_count(const ngu_epi* h);
 int ngu_epi_scan_geometry(const ngu_epi* h, int32_t out[6]);
 
+/* Measurement aid (bench.py "roofline"): bracket the next `max_calls` launches of
+ * the scan kernel (kernel A alone, not the merge) with CUDA events on the launching
+ * stream; _end synchronises and returns the summed device time and the number of
+ * launches timed. */
+int ngu_epi_scan_timing_begin(ngu_epi* h, int32_t max_calls);
+int ngu_epi_scan_timing_end(ngu_epi* h, double* total_ms, int32_t* calls);
+
 #ifdef __cplusplus
 }
 #endif

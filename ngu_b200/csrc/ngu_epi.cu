@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/ngu_epi.h"
 #include "epilogue.cuh"
@@ -92,6 +93,9 @@ struct ngu_epi {
     int64_t total_tiles = 0;
     bool scanned = false;
     int64_t launches = 0;
+    // optional per-launch timing of kernel A (bench.py roofline)
+    std::vector<cudaEvent_t> t_beg, t_end;
+    size_t t_used = 0;
     std::string err;
 };
 
@@ -265,6 +269,8 @@ void ngu_epi_destroy(ngu_epi* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
+    for (cudaEvent_t e : h->t_beg) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->t_end) cudaEventDestroy(e);
     if (h->owns_memory) cudaFree(h->memory);
     cudaFree(h->partial); cudaFree(h->topk_d2); cudaFree(h->topk_idx); cudaFree(h->dist);
     cudaFree(h->rank_sums); cudaFree(h->log_sums); cudaFree(h->state);
@@ -295,7 +301,10 @@ int ngu_epi_scan(ngu_epi* h, const float* q_dev, void* stream) {
     sp.tiles_per_actor = h->tiles_per_actor; sp.tiles_per_warp = h->tiles_per_warp;
     sp.max_parts = h->max_parts; sp.total_tiles = h->total_tiles;
     void* args[] = {&h->tmap, &sp};
+    const bool timed = h->t_used < h->t_beg.size();
+    if (timed) CU_TRY(h, cudaEventRecord(h->t_beg[h->t_used], s));
     CU_TRY(h, cudaLaunchKernel(h->var.fn, dim3(h->grid), dim3(h->var.warps * 32), args, h->var.smem, s));
+    if (timed) CU_TRY(h, cudaEventRecord(h->t_end[h->t_used++], s));
 
     MergeParams mp{};
     mp.partial = h->partial; mp.topk_d2 = h->topk_d2; mp.topk_idx = h->topk_idx; mp.dist = h->dist;
@@ -504,6 +513,43 @@ int ngu_epi_dump_memory_host(ngu_epi* h, float* slot_major_host) {
 }
 
 int64_t ngu_epi_launch_count(const ngu_epi* h) { return h ? h->launches : 0; }
+
+static void drop_timing(ngu_epi* h) {
+    for (cudaEvent_t e : h->t_beg) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->t_end) cudaEventDestroy(e);
+    h->t_beg.clear(); h->t_end.clear(); h->t_used = 0;
+}
+
+int ngu_epi_scan_timing_begin(ngu_epi* h, int32_t max_calls) {
+    if (!h || max_calls < 1) return fail(h, NGU_EINVAL, "bad argument");
+    int rc = bind_device(h);
+    if (rc) return rc;
+    drop_timing(h);
+    for (int i = 0; i < max_calls; ++i) {
+        cudaEvent_t a, b;
+        CU_TRY(h, cudaEventCreate(&a));
+        CU_TRY(h, cudaEventCreate(&b));
+        h->t_beg.push_back(a); h->t_end.push_back(b);
+    }
+    return NGU_OK;
+}
+
+int ngu_epi_scan_timing_end(ngu_epi* h, double* total_ms, int32_t* calls) {
+    if (!h || !total_ms || !calls) return fail(h, NGU_EINVAL, "null argument");
+    int rc = bind_device(h);
+    if (rc) return rc;
+    CU_TRY(h, cudaDeviceSynchronize());
+    double tot = 0.0;
+    for (size_t i = 0; i < h->t_used; ++i) {
+        float ms = 0.f;
+        CU_TRY(h, cudaEventElapsedTime(&ms, h->t_beg[i], h->t_end[i]));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *calls = static_cast<int32_t>(h->t_used);
+    drop_timing(h);
+    return NGU_OK;
+}
 
 int ngu_epi_scan_geometry(const ngu_epi* h, int32_t out[6]) {
     if (!h || !out) return NGU_EINVAL;

@@ -205,6 +205,15 @@ class EpisodicEngine:
     def launch_count(self) -> int:
         return int(self._lib.ngu_epi_launch_count(self._h))
 
+    def scan_timing_begin(self, max_calls: int):
+        check(self._lib.ngu_epi_scan_timing_begin(self._h, int(max_calls)), self._h)
+
+    def scan_timing_end(self):
+        """(total device ms of the timed scan-kernel launches, number of launches)."""
+        ms, n = C.c_double(), C.c_int32()
+        check(self._lib.ngu_epi_scan_timing_end(self._h, C.byref(ms), C.byref(n)), self._h)
+        return ms.value, n.value
+
     def scan_geometry(self) -> dict:
         g = (C.c_int32 * 6)()
         check(self._lib.ngu_epi_scan_geometry(self._h, g), self._h)

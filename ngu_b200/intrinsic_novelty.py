@@ -1,0 +1,53 @@
+"""Drop-in ``IntrinsicNovelty`` (reference: ngu/models/intrinsic_novelty/intrinsic_novelty.py:9-55).
+
+``compute_intrinsic_novelty(obs)`` keeps the reference signature (CPU float
+observations in, ``(B, 1)`` CPU tensor out) so ``NGUAgent.collect_sequence``
+(ngu/models/ngu/ngu_agent.py:74,86) can use it unchanged.  The clip of the RND
+modulator to [1, L] and the product with the episodic reward (reference lines
+26-31) are part of the engine's fused finish kernel.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import pytorch_util as ptu
+from .episodic_novelty import EpisodicNovelty
+from .lifelong_novelty import LifelongNovelty
+from .running_mean_std import DeviceRunningMeanStd
+
+
+class IntrinsicNovelty:
+    def __init__(self, n_actors, n_act, obs_shape, model_hypr, logger, mode="reference"):
+        self.logger = logger
+        self.ll_novel = LifelongNovelty(obs_shape, model_hypr, logger)
+        self.epi_novel = EpisodicNovelty(n_actors, n_act, obs_shape, model_hypr, logger, mode=mode)
+        self.max_rew = 5.0                                        # L, intrinsic_novelty.py:16
+        self.intrinsic_novel_rms = DeviceRunningMeanStd(self.epi_novel, "intr", False, 1e-4)
+        self.update_count = 0
+
+    @torch.no_grad()
+    def compute_intrinsic_novelty(self, obs):
+        alpha = self.ll_novel.compute_lifelong_curiosity(obs)      # alpha_t, CPU (reference semantics)
+        eng = self.epi_novel._ensure_engine()
+        alpha_dev = torch.as_tensor(alpha).to(device=eng.device, dtype=torch.float32)
+        r_int, _ = self.epi_novel._step(obs, alpha_dev)            # fused: r_epi * clip(alpha, 1, L)
+        return r_int.cpu().unsqueeze(-1)
+
+    def reset_memory_if_done(self, done):
+        """intrinsic_novelty.py:36-40: zero the episodic memory of finished actors."""
+        done = torch.as_tensor(done)
+        if bool(done.any()):
+            self.epi_novel._ensure_engine().reset(done)
+
+    def to(self, device):
+        self.epi_novel.to(device)
+        self.ll_novel.to(ptu.device)
+        return self
+
+    def step(self, timestep_obs, timestep_next_obs, timestep_act):
+        self.ll_novel.step(timestep_obs)
+        self.epi_novel.step(timestep_obs, timestep_next_obs, timestep_act)
+        self.update_count += 1
+        self.logger.log_scalar("IntrinsicNoveltyMean", self.intrinsic_novel_rms.mean, self.update_count)
+        self.logger.log_scalar("IntrinsicNoveltyVar", self.intrinsic_novel_rms.var, self.update_count)
