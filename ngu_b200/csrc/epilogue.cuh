@@ -1,5 +1,5 @@
-// epilogue.cuh — kernel B (merge partial lists -> per-actor k-NN, rank sums) and
-// kernel C (running-mean update + reward epilogue), plus append / reset.
+// epilogue.cuh — kernel B (rank sums, running-mean update, reward epilogue, append in
+// one single-CTA launch), plus the standalone append / reset / layout kernels.
 //
 // Reference lines replaced (ngu/models/intrinsic_novelty/...):
 //   episodic_novelty.py:54      topk (final merge of the per-warp lists)
@@ -24,10 +24,9 @@ struct DevState {
     double ed_count;
     double epi_mean, epi_var, epi_count;
     double intr_mean, intr_var, intr_count;
+    long long steps;     // the 8 words from ed_count to steps are staged together by the epilogue
     long long cursor;
-    long long steps;
-    unsigned int merge_ticket;   // last-block election for kernel B
-    unsigned int pad;
+    long long pad;
 };
 
 struct EpiConsts {
@@ -36,248 +35,324 @@ struct EpiConsts {
 };
 
 // ---------------------------------------------------------------------------
+// Code-size discipline: this kernel runs ONE CTA once per step, so its cost is
+// dominated by cold instruction fetches (its code is evicted from L2 by the 1 GB
+// scan between two launches).  Every IEEE-correct division / sqrt / reciprocal is
+// therefore a single out-of-line routine, loops are not unrolled, and the pairwise
+// summation is driven by a small host-built plan instead of recursion.
+// ---------------------------------------------------------------------------
+__device__ __noinline__ float f32_div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __noinline__ float f32_rcp(float a) { return __frcp_rn(a); }
+__device__ __noinline__ float f32_sqrt(float a) { return __fsqrt_rn(a); }
+__device__ __noinline__ double f64_div(double a, double b) { return a / b; }
+
+// ---------------------------------------------------------------------------
 // numpy's float32 pairwise summation (x.sum(axis=0), mpi_util.py:11) over one
 // column v[b*stride], b = 0..n-1, evaluated cooperatively by an aligned group of
 // 8 lanes (lane8 = lane & 7).  numpy: leaves of <= 128 elements use eight strided
 // accumulators r[0..7] combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) and a
-// sequential tail; larger n splits at n/2 rounded down to a multiple of 8.
-// Here lane a owns accumulator r[a]; the combine is three xor-shuffles (float
-// add is commutative, so every lane of the group ends with the same bits).
-// All 32 lanes of the warp must call this with the same n.
+// sequential tail; larger n splits at n/2 rounded down to a multiple of 8,
+// recursively.  The recursion is flattened on the host into a postfix plan of
+// (offset, length) leaves and (-1, 0) "add the two top values" entries
+// (build_pairwise_plan in ngu_epi.cu).  Lane a owns accumulator r[a]; the combine is
+// three xor-shuffles (float add commutes, so every lane ends with the same bits).
+// All 32 lanes of a warp must call this together.
 // ---------------------------------------------------------------------------
-__device__ inline float np_pairwise_leaf8(const float* v, int stride, int n, int lane8) {
+__device__ __noinline__ float np_pairwise_leaf8(const float* v, int stride, int n, int lane8) {
+    float r;
+    int i;
     if (n < 8) {
-        float r = -0.0f;
-        for (int i = 0; i < n; ++i) r = __fadd_rn(r, __ldcg(v + static_cast<int64_t>(i) * stride));
-        return r;
-    }
-    const int lim = n - (n % 8);
-    float r = __ldcg(v + static_cast<int64_t>(lane8) * stride);
+        r = -0.0f;
+        i = 0;
+    } else {
+        const int lim = n - (n % 8);
+        r = v[lane8 * stride];
 #pragma unroll 4
-    for (int i = 8; i < lim; i += 8) r = __fadd_rn(r, __ldcg(v + static_cast<int64_t>(i + lane8) * stride));
-    r = __fadd_rn(r, __shfl_xor_sync(kFull, r, 1));
-    r = __fadd_rn(r, __shfl_xor_sync(kFull, r, 2));
-    r = __fadd_rn(r, __shfl_xor_sync(kFull, r, 4));
-    for (int i = lim; i < n; ++i) r = __fadd_rn(r, __ldcg(v + static_cast<int64_t>(i) * stride));
+        for (i = 8; i < lim; i += 8) r = __fadd_rn(r, v[(i + lane8) * stride]);
+        r = __fadd_rn(r, __shfl_xor_sync(kFull, r, 1));
+        r = __fadd_rn(r, __shfl_xor_sync(kFull, r, 2));
+        r = __fadd_rn(r, __shfl_xor_sync(kFull, r, 4));
+    }
+#pragma unroll 1
+    for (; i < n; ++i) r = __fadd_rn(r, v[i * stride]);
     return r;
 }
-__device__ inline float np_pairwise_sum8(const float* v, int stride, int n, int lane8) {
-    if (n <= 128) return np_pairwise_leaf8(v, stride, n, lane8);
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    const float lo = np_pairwise_sum8(v, stride, n2, lane8);
-    const float hi = np_pairwise_sum8(v + static_cast<int64_t>(n2) * stride, stride, n - n2, lane8);
-    return __fadd_rn(lo, hi);
+
+constexpr int kPlanMaxDepth = 24;
+
+__device__ __forceinline__ float np_pairwise_sum8(const float* v, int stride, const int2* plan, int plan_len,
+                                                  int lane8, float* stack /* [kPlanMaxDepth] per thread */) {
+    int sp = 0;
+#pragma unroll 1
+    for (int i = 0; i < plan_len; ++i) {
+        const int2 e = plan[i];
+        if (e.y > 0) {
+            stack[sp++] = np_pairwise_leaf8(v + e.x * stride, stride, e.y, lane8);
+        } else {
+            --sp;
+            stack[sp - 1] = __fadd_rn(stack[sp - 1], stack[sp]);
+        }
+    }
+    return stack[0];
 }
 
 // ---------------------------------------------------------------------------
-// Kernel B: one warp per actor merges that actor's partial lists; the last CTA
-// to finish reduces the (B,k) distance matrix to this shard's rank sums.
+// Kernel B (epilogue): ONE CTA, launched with programmatic dependent launch right
+// behind the scan kernel, so it is already resident when the scan drains.
+// Phases (bitmask, so the same code serves the single-shard step and the split
+// scan | exchange | finish sequence of a multi-GPU step):
+//   RANKSUMS  column sums of this shard's (B,k) k-NN distance matrix
+//             = mpi_mean's localsum (mpi_util.py:11-15)
+//   FINISH    RunningMeanStd update from the (global) sums (mpi_util.py:48-73),
+//             per-actor reward (episodic_novelty.py:58-78), RND multiplier clip and
+//             product (intrinsic_novelty.py:26-31), log-only batch sums
+//   APPEND    insert_state (episodic_novelty.py:86-89)
 // ---------------------------------------------------------------------------
-struct MergeParams {
-    const u64* partial;      // [B][max_parts][k]
-    float* topk_d2;          // [B][k]
-    int32_t* topk_idx;       // [B][k]
-    float* dist;             // [B][k]  sqrt(d2) (reference) or d2 (paper)
-    double* rank_sums;       // [2k+1]
+enum : int { PH_RANKSUMS = 1, PH_FINISH = 2, PH_APPEND = 4, PH_LOGFUSE = 8 };
+
+struct EpilogueParams {
+    const float* dist;        // [B][k]  sqrt(d2) (reference) or d2 (paper), written by the scan kernel
+    double* rank_sums;        // [2k+1]  out (RANKSUMS)
+    const double* sums_in;    // [2k+1]  global sums for FINISH; null = the sums computed in this launch
+    const float* alpha;       // [B] or null
+    float* r_int;             // [B]
+    float* r_epi;             // [B] or null
+    double* log_sums;         // [5] or null
+    const float* q;           // [B][32] (APPEND)
+    float* memory;            // [B][N][32] (APPEND)
     DevState* state;
-    int32_t tiles_per_actor, tiles_per_warp, max_parts, pad;
-};
-
-template <int WARPS>   // WARPS*32 >= 8*k is required (8 lanes per column in the rank-sum pass)
-__global__ void __launch_bounds__(WARPS * 32) merge_topk_kernel(const MergeParams p, const EpiConsts c) {
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int b = blockIdx.x * WARPS + warp;
-    const int k = c.k;
-    const bool largest = c.largest != 0;
-
-    if (b < c.n_actors) {
-        const int64_t t0 = static_cast<int64_t>(b) * p.tiles_per_actor;
-        const int first = static_cast<int>(t0 / p.tiles_per_warp);
-        const int last = static_cast<int>((t0 + p.tiles_per_actor - 1) / p.tiles_per_warp);
-        const int nkeys = (last - first + 1) * k;
-        const u64* base = p.partial + static_cast<int64_t>(b) * p.max_parts * k;
-        WarpTopK top;
-        top.reset();
-        for (int i0 = 0; i0 < nkeys; i0 += 32) {
-            const int i = i0 + lane;
-            const u64 key = i < nkeys ? base[i] : 0ull;
-            top.offer(key, lane, k);
-        }
-        if (lane < k) {
-            const float d2 = key_d2(top.lkey, largest);
-            p.topk_d2[b * k + lane] = d2;
-            p.topk_idx[b * k + lane] = key_slot(top.lkey);
-            p.dist[b * k + lane] = c.sqrt_dist ? __fsqrt_rn(d2) : d2;
-        }
-    }
-
-    // ---- last-CTA election (threadfence reduction) ----
-    __shared__ bool is_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned ticket = atomicAdd(&p.state->merge_ticket, 1u);
-        is_last = (ticket == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    if (threadIdx.x == 0) p.state->merge_ticket = 0;  // re-arm for the next step
-
-    // Rank sums (mpi_mean's localsum, mpi_util.py:11-15): column sums of the
-    // (B,k) matrix in numpy's pairwise f32 order, then sum of squares in f64
-    // for the (log-only) variance, then the row count.
-    const int B = c.n_actors;
-    const int group = threadIdx.x >> 3, lane8 = threadIdx.x & 7;   // 8 lanes per column
-    const int j = group < k ? group : k - 1;                       // idle groups shadow column k-1
-    const float s1 = np_pairwise_sum8(p.dist + j, k, B, lane8);
-    double s2 = 0.0;
-    for (int bb = lane8; bb < B; bb += 8) {
-        const double v = static_cast<double>(__ldcg(p.dist + static_cast<int64_t>(bb) * k + j));
-        s2 += v * v;
-    }
-    s2 += __shfl_xor_sync(kFull, s2, 1);
-    s2 += __shfl_xor_sync(kFull, s2, 2);
-    s2 += __shfl_xor_sync(kFull, s2, 4);
-    if (group < k && lane8 == 0) {
-        p.rank_sums[group] = static_cast<double>(s1);
-        p.rank_sums[k + group] = s2;
-    }
-    if (threadIdx.x == 0) p.rank_sums[2 * k] = static_cast<double>(B);
-}
-
-// ---------------------------------------------------------------------------
-// Kernel C: RunningMeanStd update (mpi_util.py:48-73) from the global rank sums,
-// then the per-actor reward (episodic_novelty.py:58-78, intrinsic_novelty.py:26-31).
-// Single CTA; B is at most a few thousand actors per shard.
-// ---------------------------------------------------------------------------
-struct FinishParams {
-    const float* dist;       // [B][k]
-    const double* sums;      // [2k+1] global
-    const float* alpha;      // [B] or null
-    float* r_int;            // [B]
-    float* r_epi;            // [B] or null
-    double* log_sums;        // [5] or null
-    DevState* state;
-    int32_t fuse_log_update; // 1: apply the log-only rms updates here (single shard)
+    const int2* plan;         // pairwise-sum plan for n = B
+    int32_t plan_len;
+    int32_t phases;
+    int32_t stage_q;          // 1: q fits the dynamic shared memory of this launch
     int32_t pad;
 };
+
+// Chan/Welford merge of (mean, var, count) with a batch (mpi_util.py:59-73), all f64.
+__device__ __noinline__ void rms_merge(double* mean, double* var, double* count, double b_mean, double b_var,
+                                       double b_count) {
+    const double delta = b_mean - *mean;
+    const double tot = *count + b_count;
+    const double m2 = *var * *count + b_var * b_count + f64_div(delta * delta * *count * b_count, tot);
+    *mean = *mean + f64_div(delta * b_count, tot);
+    *var = f64_div(m2, tot);
+    *count = tot;
+}
+
+// sc = {epi_mean, epi_var, epi_count, intr_mean, intr_var, intr_count} (the DevState order)
+__device__ __noinline__ void log_rms_apply(double* sc, const double* ls) {
+    const double n = ls[4];
+    if (n > 0.0) {
+        const double m1 = f64_div(ls[0], n), v1 = fmax(f64_div(ls[1], n) - m1 * m1, 0.0);
+        rms_merge(&sc[0], &sc[1], &sc[2], m1, v1, n);
+        const double m2 = f64_div(ls[2], n), v2 = fmax(f64_div(ls[3], n) - m2 * m2, 0.0);
+        rms_merge(&sc[3], &sc[4], &sc[5], m2, v2, n);
+    }
+}
+__device__ __forceinline__ long long st_steps_plus_one(double raw) { return __double_as_longlong(raw) + 1; }
 
 // torch.max(x, 0) semantics (NaN propagates), episodic_novelty.py:60-65
 __device__ __forceinline__ float relu_nanprop(float x) { return (x != x) ? x : (x > 0.0f ? x : 0.0f); }
 
-// Chan/Welford merge of (mean, var, count) with a batch (mpi_util.py:59-73), all f64.
-__device__ inline void rms_merge(double& mean, double& var, double& count, double b_mean, double b_var,
-                                 double b_count) {
-    const double delta = b_mean - mean;
-    const double tot = count + b_count;
-    const double new_mean = mean + delta * b_count / tot;
-    const double m2 = var * count + b_var * b_count + delta * delta * count * b_count / tot;
-    mean = new_mean;
-    var = m2 / tot;
-    count = tot;
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-__device__ inline void log_rms_apply(DevState* st, const double* ls) {
-    const double n = ls[4];
-    if (n > 0.0) {
-        const double m1 = ls[0] / n, v1 = fmax(ls[1] / n - m1 * m1, 0.0);
-        rms_merge(st->epi_mean, st->epi_var, st->epi_count, m1, v1, n);
-        const double m2 = ls[2] / n, v2 = fmax(ls[3] / n - m2 * m2, 0.0);
-        rms_merge(st->intr_mean, st->intr_var, st->intr_count, m2, v2, n);
-    }
+// Dynamic shared memory of the epilogue: [dist B*k][alpha B][q B*32] floats.
+__host__ __device__ inline size_t epilogue_q_offset(int B, int k) {   // floats; keeps q 16-byte aligned
+    return (static_cast<size_t>(B) * (k + 1) + 3) & ~static_cast<size_t>(3);
+}
+__host__ __device__ inline size_t epilogue_smem_bytes(int B, int k, bool with_q) {
+    return (epilogue_q_offset(B, k) + (with_q ? static_cast<size_t>(B) * 32 : 0)) * sizeof(float);
 }
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) finish_kernel(const FinishParams p, const EpiConsts c) {
+template <int THREADS>   // THREADS >= 8 * NGU_EPI_MAX_K (8 lanes per column in the rank-sum pass)
+__global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams p, const EpiConsts c) {
+    __shared__ double s_sums[2 * 32 + 1];
+    __shared__ double s_mean[32], s_var[32];
+    __shared__ double s_scal[8];      // ed_count, epi(mean,var,count), intr(mean,var,count), steps
     __shared__ float mean32[32];
     __shared__ double red[4][THREADS / 32];
-    __shared__ double tot[4];
+    __shared__ long long s_cursor;
+    __shared__ int2 s_plan[64];
+    __shared__ float s_stack[256][kPlanMaxDepth + 1];   // value stacks of the rank-sum threads (padded)
+    extern __shared__ float s_dyn[];
     const int k = c.k;
+    const int B = c.n_actors;
+    float* s_dist = s_dyn;                 // [B][k]
+    float* s_alpha = s_dist + B * k;       // [B]
+    float4* s_q = reinterpret_cast<float4*>(s_dyn + epilogue_q_offset(B, k));   // [B][8]
     DevState* st = p.state;
+    const bool finish = (p.phases & PH_FINISH) != 0, append = (p.phases & PH_APPEND) != 0;
 
-    if (threadIdx.x < k) {
-        const int j = threadIdx.x;
-        const double cnt = p.sums[2 * k];
-        const float cnt32 = static_cast<float>(cnt);
-        // mpi_mean: globalsum[:n] / globalsum[n] in float32 (mpi_util.py:18)
-        const float b_mean = __fdiv_rn(static_cast<float>(p.sums[j]), cnt32);
-        // mpi_moments' second pass (mpi_util.py:25-28) from the f64 sum of squares:
-        // E[(x-m)^2] = E[x^2] - 2 m E[x] + m^2 with m the f32 batch mean.
-        const double ex = p.sums[j] / cnt, ex2 = p.sums[k + j] / cnt, bm = static_cast<double>(b_mean);
-        const float msd = static_cast<float>(fmax(ex2 - 2.0 * bm * ex + bm * bm, 0.0));
-        const float b_std = __fsqrt_rn(msd);
-        const float b_var = __fmul_rn(b_std, b_std);                 // np.square(batch_std), :56
-        const double m_b = static_cast<double>(__fmul_rn(b_var, cnt32));  // batch_var * batch_count (f32), :65
-        const double count = st->ed_count;
-        const double delta = bm - st->ed_mean[j];
-        const double totc = count + static_cast<double>(cnt32);
-        const double new_mean = st->ed_mean[j] + delta * static_cast<double>(cnt32) / totc;
-        const double m2 = st->ed_var[j] * count + m_b +
-                          delta * delta * count * static_cast<double>(cnt32) / totc;
-        st->ed_mean[j] = new_mean;
-        st->ed_var[j] = m2 / totc;
-        mean32[j] = static_cast<float>(new_mean);                    // ptu.to_tensor(...).float(), pytorch_util.py:20
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // next step's scan may start its prologue
+
+    // While the scan is still streaming: pull this kernel's small inputs into L2 (the scan's TMA
+    // traffic is tagged evict-first, so they stay there).  L2 is the coherence point, so
+    // prefetching lines that the previous epilogue may still be writing is harmless.
+    if (threadIdx.x < 5) prefetch_l2(reinterpret_cast<const char*>(st) + 128 * threadIdx.x);
+    if (threadIdx.x == 5) prefetch_l2(p.plan);
+    if (finish && p.alpha)
+        for (int i = threadIdx.x * 32; i < B; i += THREADS * 32) prefetch_l2(p.alpha + i);
+    if (append)
+        for (int i = threadIdx.x; i < B; i += THREADS) prefetch_l2(p.q + static_cast<int64_t>(i) * 32);
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // scan kernel complete, its writes visible
+
+    // ---- one batch of independent loads: everything the phases below need goes on chip ----
+#pragma unroll 1
+    for (int i = threadIdx.x; i < B * k; i += THREADS) s_dist[i] = __ldcg(p.dist + i);
+    if (finish) {
+#pragma unroll 1
+        for (int i = threadIdx.x; i < B; i += THREADS) s_alpha[i] = p.alpha ? __ldcg(p.alpha + i) : 1.0f;
+        if (p.sums_in && threadIdx.x < 2 * k + 1) s_sums[threadIdx.x] = __ldcg(p.sums_in + threadIdx.x);
+        if (threadIdx.x < k) {
+            s_mean[threadIdx.x] = __ldcg(&st->ed_mean[threadIdx.x]);
+            s_var[threadIdx.x] = __ldcg(&st->ed_var[threadIdx.x]);
+        }
+        if (threadIdx.x >= 32 && threadIdx.x < 40) s_scal[threadIdx.x - 32] = __ldcg(&st->ed_count + (threadIdx.x - 32));
     }
+    if (append) {
+        if (p.stage_q) {
+#pragma unroll 1
+            for (int i = threadIdx.x; i < B * 8; i += THREADS) s_q[i] = __ldcg(reinterpret_cast<const float4*>(p.q) + i);
+        }
+        if (threadIdx.x == 64) s_cursor = __ldcg(&st->cursor);
+    }
+    if (threadIdx.x >= 96 && threadIdx.x < 96 + p.plan_len && threadIdx.x < 160) s_plan[threadIdx.x - 96] = __ldcg(p.plan + (threadIdx.x - 96));
     __syncthreads();
-    if (threadIdx.x == 0) {
-        st->ed_count = st->ed_count + static_cast<double>(static_cast<float>(p.sums[2 * k]));
-        st->steps += 1;
+
+    if (p.phases & PH_RANKSUMS) {
+        if (threadIdx.x < 256) {
+            // column sums in numpy's pairwise order: 8 lanes per column (whole warps: shuffles inside)
+            const int group = threadIdx.x >> 3, lane8 = threadIdx.x & 7;
+            const int j = group < k ? group : k - 1;                   // idle groups shadow column k-1
+            const float s1 = np_pairwise_sum8(s_dist + j, k, s_plan, p.plan_len, lane8, s_stack[threadIdx.x]);
+            if (group < k && lane8 == 0) s_sums[group] = static_cast<double>(s1);
+        } else {
+            // meanwhile: f64 sums of squares (for the log-only variance), a full warp per column
+            const int lane = threadIdx.x & 31;
+#pragma unroll 1
+            for (int j = (threadIdx.x >> 5) - 8; j < k; j += (THREADS - 256) / 32) {
+                double s2 = 0.0;
+#pragma unroll 4
+                for (int bb = lane; bb < B; bb += 32) {
+                    const double v = static_cast<double>(s_dist[bb * k + j]);
+                    s2 += v * v;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(kFull, s2, o);
+                if (lane == 0) s_sums[k + j] = s2;
+            }
+        }
+        if (threadIdx.x == 0) s_sums[2 * k] = static_cast<double>(B);
+        __syncthreads();
+        if (threadIdx.x < 2 * k + 1) p.rank_sums[threadIdx.x] = s_sums[threadIdx.x];
     }
 
-    double s_e = 0.0, s_e2 = 0.0, s_i = 0.0, s_i2 = 0.0;
-    for (int b = threadIdx.x; b < c.n_actors; b += THREADS) {
-        float acc = 0.0f;
-        for (int j = 0; j < k; ++j) {
-            const float v = p.dist[b * k + j];
-            const float nd = __fdiv_rn(v, mean32[j]);                          // :58
-            const float cl = relu_nanprop(__fsub_rn(nd, c.cluster));           // :60-65
-            const float kv = __fmul_rn(__frcp_rn(__fadd_rn(cl, c.eps)), c.eps); // :67-68 (reciprocal()*eps)
-            acc = (j == 0) ? kv : __fadd_rn(acc, kv);                          // :71 sum(dim=0)
+    if (finish) {
+        if (threadIdx.x < k) {
+            const int j = threadIdx.x;
+            const double cnt = s_sums[2 * k];
+            const float cnt32 = static_cast<float>(cnt);
+            // mpi_mean: globalsum[:n] / globalsum[n] in float32 (mpi_util.py:18)
+            const float b_mean = f32_div(static_cast<float>(s_sums[j]), cnt32);
+            // mpi_moments' second pass (mpi_util.py:25-28) from the f64 sum of squares:
+            // E[(x-m)^2] = E[x^2] - 2 m E[x] + m^2 with m the f32 batch mean.
+            const double ex = f64_div(s_sums[j], cnt), ex2 = f64_div(s_sums[k + j], cnt), bm = static_cast<double>(b_mean);
+            const float msd = static_cast<float>(fmax(ex2 - 2.0 * bm * ex + bm * bm, 0.0));
+            const float b_std = f32_sqrt(msd);
+            const float b_var = __fmul_rn(b_std, b_std);                      // np.square(batch_std), :56
+            const double m_b = static_cast<double>(__fmul_rn(b_var, cnt32)); // batch_var * batch_count (f32), :65
+            const double count = s_scal[0];
+            const double n_b = static_cast<double>(cnt32);
+            const double delta = bm - s_mean[j];
+            const double totc = count + n_b;
+            const double new_mean = s_mean[j] + f64_div(delta * n_b, totc);
+            const double m2 = s_var[j] * count + m_b + f64_div(delta * delta * count * n_b, totc);
+            st->ed_mean[j] = new_mean;
+            st->ed_var[j] = f64_div(m2, totc);
+            mean32[j] = static_cast<float>(new_mean);   // ptu.to_tensor(...).float(), pytorch_util.py:20
         }
-        const float sim = __fadd_rn(__fsqrt_rn(acc), c.pseudo);                // :71-72
-        float r = __frcp_rn(sim);                                              // :75
-        if (sim > c.s_max) r = 0.0f;                                           // :76-78
-        float a = p.alpha ? p.alpha[b] : 1.0f;
-        if (a < 1.0f) a = 1.0f;                                                // intrinsic_novelty.py:26-27
-        if (a > c.max_rew) a = c.max_rew;                                      // :28-29
-        const float ri = __fmul_rn(r, a);                                      // :31
-        if (p.r_epi) p.r_epi[b] = r;
-        p.r_int[b] = ri;
-        s_e += r; s_e2 += static_cast<double>(r) * r;
-        s_i += ri; s_i2 += static_cast<double>(ri) * ri;
+        if (threadIdx.x == 32) {
+            st->ed_count = s_scal[0] + static_cast<double>(static_cast<float>(s_sums[2 * k]));
+            st->steps = st_steps_plus_one(s_scal[7]);
+        }
+        __syncthreads();
+
+        double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+        for (int b = threadIdx.x; b < B; b += THREADS) {
+            float acc = 0.0f;
+#pragma unroll 5
+            for (int j = 0; j < k; ++j) {   // iterations are independent up to the final add: unrolled for ILP
+                const float nd = __fdiv_rn(s_dist[b * k + j], mean32[j]);           // :58
+                const float cl = relu_nanprop(__fsub_rn(nd, c.cluster));            // :60-65
+                const float kv = __fmul_rn(__frcp_rn(__fadd_rn(cl, c.eps)), c.eps); // :67-68 (reciprocal()*eps)
+                acc = (j == 0) ? kv : __fadd_rn(acc, kv);                           // :71 sum(dim=0)
+            }
+            const float sim = __fadd_rn(f32_sqrt(acc), c.pseudo);                   // :71-72
+            float r = f32_rcp(sim);                                                 // :75
+            if (sim > c.s_max) r = 0.0f;                                            // :76-78
+            float a = s_alpha[b];
+            if (a < 1.0f) a = 1.0f;                                                 // intrinsic_novelty.py:26-27
+            if (a > c.max_rew) a = c.max_rew;                                       // :28-29
+            const float ri = __fmul_rn(r, a);                                       // :31
+            if (p.r_epi) p.r_epi[b] = r;
+            p.r_int[b] = ri;
+            acc4[0] += r; acc4[1] += static_cast<double>(r) * r;
+            acc4[2] += ri; acc4[3] += static_cast<double>(ri) * ri;
+        }
+
+        // log-only batch sums (epi_novel_rms / intrinsic_novel_rms), fixed-order tree
+        if (p.log_sums || (p.phases & PH_LOGFUSE)) {
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                double v = acc4[q];
+#pragma unroll 1
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+                if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v;
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                // lanes 0..15 hold one warp partial each; 4 quantities reduced by shuffles
+                double ls[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    double v = threadIdx.x < THREADS / 32 ? red[q][threadIdx.x] : 0.0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+                    ls[q] = v;
+                }
+                const double n = static_cast<double>(B);
+                if (p.log_sums && threadIdx.x < 5) p.log_sums[threadIdx.x] = threadIdx.x < 4 ? ls[threadIdx.x] : n;
+                if ((p.phases & PH_LOGFUSE) && threadIdx.x < 2) {
+                    // lane 0: epi_novel_rms, lane 1: intrinsic_novel_rms (staged in s_scal[1..6])
+                    const int o = 2 * threadIdx.x;
+                    const double m = f64_div(ls[o], n), v = fmax(f64_div(ls[o + 1], n) - m * m, 0.0);
+                    double* sc = s_scal + 1 + 3 * threadIdx.x;
+                    rms_merge(&sc[0], &sc[1], &sc[2], m, v, n);
+                    for (int q = 0; q < 3; ++q) (&st->ed_count)[1 + 3 * threadIdx.x + q] = sc[q];
+                }
+            }
+        }
     }
 
-    // log-only batch sums (epi_novel_rms / intrinsic_novel_rms), fixed-order tree
-    if (p.log_sums || p.fuse_log_update) {
-        double vals[4] = {s_e, s_e2, s_i, s_i2};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            double v = vals[q];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-            if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v;
+    if (append) {
+        const long long cur = s_cursor;
+        const float4* q4 = reinterpret_cast<const float4*>(p.q);
+#pragma unroll 1
+        for (int i = threadIdx.x; i < B * 8; i += THREADS) {
+            const int b = i >> 3, ch = i & 7;
+            float4* dst = reinterpret_cast<float4*>(p.memory + (static_cast<int64_t>(b) * c.capacity + cur) * 32) + ch;
+            *dst = p.stage_q ? s_q[i] : __ldcg(q4 + i);
         }
-        __syncthreads();
-        if (threadIdx.x < 4) {
-            double v = 0.0;
-            for (int w = 0; w < THREADS / 32; ++w) v += red[threadIdx.x][w];
-            tot[threadIdx.x] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double ls[5] = {tot[0], tot[1], tot[2], tot[3], static_cast<double>(c.n_actors)};
-            if (p.log_sums)
-                for (int q = 0; q < 5; ++q) p.log_sums[q] = ls[q];
-            if (p.fuse_log_update) log_rms_apply(st, ls);
-        }
+        if (threadIdx.x == 64) st->cursor = (cur + 1) % c.capacity;
     }
 }
 
 __global__ void log_update_kernel(DevState* st, const double* log_sums) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) log_rms_apply(st, log_sums);
+    if (threadIdx.x == 0 && blockIdx.x == 0) log_rms_apply(&st->epi_mean, log_sums);
 }
 
 // ---------------------------------------------------------------------------

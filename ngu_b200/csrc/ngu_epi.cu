@@ -2,13 +2,15 @@
 //
 // Host side of the B200 episodic-novelty engine: handle/state management, the
 // TMA tensor map over the episodic memory, launch geometry, and the per-step
-// kernel sequence  scan_topk -> merge_topk -> [exchange] -> finish -> append.
+// kernel sequence  scan_topk (with in-kernel merge) -> epilogue (rank sums, [exchange],
+// running-mean update, rewards, append), chained with programmatic dependent launch.
 // No torch headers, no CPU fallback: every entry point needs a CUDA device.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -60,8 +62,22 @@ const Variant kVariants[] = {
     make_variant<4, 6, 2>(1),   // 7:  4 warps/SM, 6 x 8 KB                         = 192 KB
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-constexpr int kMergeWarps = 8;
-constexpr int kFinishThreads = 512;
+constexpr int kEpilogueThreads = 512;
+constexpr size_t kEpilogueStageBytes = 160 * 1024;   // (B,k) f32 staged in smem: B*k <= 40960 per handle
+
+// Flatten numpy's pairwise-summation recursion for n elements into a postfix plan:
+// (offset, length) = sum that leaf and push; (-1, 0) = pop two, push their f32 sum.
+void build_pairwise_plan(int off, int n, std::vector<int2>& plan) {
+    if (n <= 128) {
+        plan.push_back(make_int2(off, n));
+        return;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    build_pairwise_plan(off, n2, plan);
+    build_pairwise_plan(off + n2, n - n2, plan);
+    plan.push_back(make_int2(-1, 0));
+}
 constexpr int kMinTilesPerWarp = 4;
 
 }  // namespace
@@ -78,7 +94,12 @@ struct ngu_epi {
     float* dist = nullptr;           // [B][k]
     double* rank_sums = nullptr;     // [2k+1]
     double* log_sums = nullptr;      // [5]
+    unsigned int* actor_arrivals = nullptr;  // [B] per-actor flush counter of the scan kernel
+    int2* plan_dev = nullptr;        // pairwise-sum plan for n = B (epilogue rank sums)
+    int plan_len = 0;
     DevState* state = nullptr;
+    bool use_pdl = true;
+    int debug_phase_mask = ~0;       // NGU_EPI_DEBUG_PHASES: experiments only (tools/sweep.py)
     // staging for the *_host entry points
     cudaStream_t own_stream = nullptr;
     float* q_stage_dev = nullptr;    // [B][32]
@@ -179,6 +200,8 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
     if (static_cast<int64_t>(cfg->n_actors) * cfg->capacity + 256 >= (1ll << 31))
         return fail(nullptr, NGU_EINVAL, "n_actors*capacity must stay below 2^31 rows per handle; shard the actors");
     if (cfg->scan_variant < 0 || cfg->scan_variant >= kNumVariants) return fail(nullptr, NGU_EINVAL, "unknown scan_variant");
+    if (epilogue_smem_bytes(cfg->n_actors, cfg->k, false) > kEpilogueStageBytes)
+        return fail(nullptr, NGU_EINVAL, "n_actors*(k+1) exceeds 40960 per handle (the epilogue stages the k-NN matrix on chip); shard the actors");
     if (memory_dev && (reinterpret_cast<uintptr_t>(memory_dev) & 127u))
         return fail(nullptr, NGU_EINVAL, "memory_dev must be 128-byte aligned (one row)");
 
@@ -220,6 +243,10 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
         return NGU_EINVAL;
     }
     CREATE_TRY(cudaFuncSetAttribute(h->var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->var.smem));
+    CREATE_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(&epilogue_kernel<kEpilogueThreads>),
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kEpilogueStageBytes)));
+    if (const char* e = getenv("NGU_EPI_PDL")) h->use_pdl = atoi(e) != 0;
+    if (const char* e = getenv("NGU_EPI_DEBUG_PHASES")) h->debug_phase_mask = atoi(e);
     plan_geometry(h);
 
     const int B = cfg->n_actors, k = cfg->k;
@@ -237,8 +264,17 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
     CREATE_TRY(cudaMalloc(&h->dist, static_cast<size_t>(B) * k * sizeof(float)));
     CREATE_TRY(cudaMalloc(&h->rank_sums, NGU_EPI_RANK_SUMS(NGU_EPI_MAX_K) * sizeof(double)));
     CREATE_TRY(cudaMalloc(&h->log_sums, 8 * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->actor_arrivals, static_cast<size_t>(B) * sizeof(unsigned int)));
+    CREATE_TRY(cudaMemset(h->actor_arrivals, 0, static_cast<size_t>(B) * sizeof(unsigned int)));
     CREATE_TRY(cudaMalloc(&h->state, sizeof(DevState)));
     CREATE_TRY(cudaMemset(h->state, 0, sizeof(DevState)));
+    {
+        std::vector<int2> plan;
+        build_pairwise_plan(0, B, plan);
+        h->plan_len = static_cast<int>(plan.size());
+        CREATE_TRY(cudaMalloc(&h->plan_dev, plan.size() * sizeof(int2)));
+        CREATE_TRY(cudaMemcpy(h->plan_dev, plan.data(), plan.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    }
     CREATE_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaMalloc(&h->q_stage_dev, static_cast<size_t>(B) * 32 * sizeof(float)));
     CREATE_TRY(cudaMalloc(&h->a_stage_dev, static_cast<size_t>(B) * sizeof(float)));
@@ -273,7 +309,7 @@ void ngu_epi_destroy(ngu_epi* h) {
     for (cudaEvent_t e : h->t_end) cudaEventDestroy(e);
     if (h->owns_memory) cudaFree(h->memory);
     cudaFree(h->partial); cudaFree(h->topk_d2); cudaFree(h->topk_idx); cudaFree(h->dist);
-    cudaFree(h->rank_sums); cudaFree(h->log_sums); cudaFree(h->state);
+    cudaFree(h->rank_sums); cudaFree(h->log_sums); cudaFree(h->state); cudaFree(h->actor_arrivals); cudaFree(h->plan_dev);
     cudaFree(h->q_stage_dev); cudaFree(h->a_stage_dev); cudaFree(h->r_stage_dev); cudaFree(h->done_stage_dev);
     if (h->pinned) cudaFreeHost(h->pinned);
     delete h;
@@ -288,32 +324,65 @@ int ngu_epi_memory(ngu_epi* h, float** memory_dev, int64_t strides[3]) {
     return NGU_OK;
 }
 
+// Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may
+// become resident before its predecessor in the stream has finished; both of our kernels
+// order themselves with griddepcontrol.wait.
+static cudaError_t launch_pdl(const void* fn, dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                              void** args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelExC(&cfg, fn, args);
+}
+
+static int launch_scan(ngu_epi* h, const float* q_dev, cudaStream_t s) {
+    ScanParams sp{};
+    sp.q = q_dev; sp.partial = h->partial;
+    sp.n_actors = h->cfg.n_actors; sp.capacity = h->cfg.capacity; sp.k = h->cfg.k;
+    sp.largest = h->consts.largest; sp.sqrt_dist = h->consts.sqrt_dist;
+    sp.tiles_per_actor = h->tiles_per_actor; sp.tiles_per_warp = h->tiles_per_warp;
+    sp.max_parts = h->max_parts; sp.total_tiles = h->total_tiles;
+    sp.actor_arrivals = h->actor_arrivals;
+    sp.topk_d2 = h->topk_d2; sp.topk_idx = h->topk_idx; sp.dist = h->dist;
+    void* args[] = {&h->tmap, &sp};
+    const bool timed = h->t_used < h->t_beg.size();
+    if (timed) CU_TRY(h, cudaEventRecord(h->t_beg[h->t_used], s));
+    CU_TRY(h, launch_pdl(h->var.fn, dim3(h->grid), dim3(h->var.warps * 32), h->var.smem, s, h->use_pdl && !timed, args));
+    if (timed) CU_TRY(h, cudaEventRecord(h->t_end[h->t_used++], s));
+    h->launches += 1;
+    return NGU_OK;
+}
+
+static int launch_epilogue(ngu_epi* h, int phases, const double* sums_in, const float* alpha, float* r_int,
+                           float* r_epi, double* log_sums, const float* q, cudaStream_t s) {
+    EpilogueParams ep{};
+    ep.dist = h->dist; ep.rank_sums = h->rank_sums; ep.sums_in = sums_in; ep.alpha = alpha;
+    ep.r_int = r_int; ep.r_epi = r_epi; ep.log_sums = log_sums; ep.q = q; ep.memory = h->memory;
+    ep.state = h->state; ep.phases = phases & h->debug_phase_mask;
+    ep.plan = h->plan_dev; ep.plan_len = h->plan_len;
+    // dynamic smem: [dist B*k][alpha B][q B*32] when it all fits, else without q
+    ep.stage_q = epilogue_smem_bytes(h->cfg.n_actors, h->cfg.k, true) <= kEpilogueStageBytes ? 1 : 0;
+    const size_t dyn = epilogue_smem_bytes(h->cfg.n_actors, h->cfg.k, ep.stage_q != 0);
+    void* args[] = {&ep, &h->consts};
+    CU_TRY(h, launch_pdl(reinterpret_cast<const void*>(&epilogue_kernel<kEpilogueThreads>), dim3(1),
+                         dim3(kEpilogueThreads), dyn, s, h->use_pdl, args));
+    h->launches += 1;
+    return NGU_OK;
+}
+
 int ngu_epi_scan(ngu_epi* h, const float* q_dev, void* stream) {
     if (!h || !q_dev) return fail(h, NGU_EINVAL, "null argument");
     int rc = bind_device(h);
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-
-    ScanParams sp{};
-    sp.q = q_dev; sp.partial = h->partial;
-    sp.n_actors = h->cfg.n_actors; sp.capacity = h->cfg.capacity; sp.k = h->cfg.k;
-    sp.largest = h->consts.largest;
-    sp.tiles_per_actor = h->tiles_per_actor; sp.tiles_per_warp = h->tiles_per_warp;
-    sp.max_parts = h->max_parts; sp.total_tiles = h->total_tiles;
-    void* args[] = {&h->tmap, &sp};
-    const bool timed = h->t_used < h->t_beg.size();
-    if (timed) CU_TRY(h, cudaEventRecord(h->t_beg[h->t_used], s));
-    CU_TRY(h, cudaLaunchKernel(h->var.fn, dim3(h->grid), dim3(h->var.warps * 32), args, h->var.smem, s));
-    if (timed) CU_TRY(h, cudaEventRecord(h->t_end[h->t_used++], s));
-
-    MergeParams mp{};
-    mp.partial = h->partial; mp.topk_d2 = h->topk_d2; mp.topk_idx = h->topk_idx; mp.dist = h->dist;
-    mp.rank_sums = h->rank_sums; mp.state = h->state;
-    mp.tiles_per_actor = h->tiles_per_actor; mp.tiles_per_warp = h->tiles_per_warp; mp.max_parts = h->max_parts;
-    const int mgrid = (h->cfg.n_actors + kMergeWarps - 1) / kMergeWarps;
-    merge_topk_kernel<kMergeWarps><<<mgrid, kMergeWarps * 32, 0, s>>>(mp, h->consts);
-    CU_TRY(h, cudaGetLastError());
-    h->launches += 2;
+    rc = launch_scan(h, q_dev, s);
+    if (rc) return rc;
+    rc = launch_epilogue(h, PH_RANKSUMS, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, s);
+    if (rc) return rc;
     h->scanned = true;
     return NGU_OK;
 }
@@ -324,27 +393,17 @@ int ngu_epi_rank_sums(ngu_epi* h, double** sums_dev) {
     return NGU_OK;
 }
 
-static int finish_impl(ngu_epi* h, const double* sums, const float* alpha, float* r_int, float* r_epi,
-                       double* log_sums, int fuse_log, cudaStream_t s) {
-    if (!h->scanned) return fail(h, NGU_ESTATE, "ngu_epi_finish called before ngu_epi_scan");
-    FinishParams fp{};
-    fp.dist = h->dist; fp.sums = sums ? sums : h->rank_sums; fp.alpha = alpha;
-    fp.r_int = r_int; fp.r_epi = r_epi; fp.log_sums = log_sums; fp.state = h->state;
-    fp.fuse_log_update = fuse_log;
-    finish_kernel<kFinishThreads><<<1, kFinishThreads, 0, s>>>(fp, h->consts);
-    CU_TRY(h, cudaGetLastError());
-    h->launches += 1;
-    h->scanned = false;
-    return NGU_OK;
-}
-
 int ngu_epi_finish(ngu_epi* h, const double* sums_global_dev, const float* alpha_dev, float* r_int_dev,
                    float* r_epi_dev, double* log_sums_dev, void* stream) {
     if (!h || !r_int_dev) return fail(h, NGU_EINVAL, "null argument");
     int rc = bind_device(h);
     if (rc) return rc;
-    return finish_impl(h, sums_global_dev, alpha_dev, r_int_dev, r_epi_dev, log_sums_dev, 0,
-                       static_cast<cudaStream_t>(stream));
+    if (!h->scanned) return fail(h, NGU_ESTATE, "ngu_epi_finish called before ngu_epi_scan");
+    rc = launch_epilogue(h, PH_FINISH, sums_global_dev ? sums_global_dev : h->rank_sums, alpha_dev, r_int_dev,
+                         r_epi_dev, log_sums_dev, nullptr, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+    h->scanned = false;
+    return NGU_OK;
 }
 
 int ngu_epi_log_update(ngu_epi* h, const double* log_sums_global_dev, void* stream) {
@@ -383,11 +442,14 @@ int ngu_epi_reset(ngu_epi* h, const uint8_t* done_dev, void* stream) {
 int ngu_epi_step(ngu_epi* h, const float* q_dev, const float* alpha_dev, float* r_int_dev, float* r_epi_dev,
                  void* stream) {
     if (!h || !q_dev || !r_int_dev) return fail(h, NGU_EINVAL, "null argument");
-    int rc = ngu_epi_scan(h, q_dev, stream);
+    int rc = bind_device(h);
     if (rc) return rc;
-    rc = finish_impl(h, nullptr, alpha_dev, r_int_dev, r_epi_dev, nullptr, 1, static_cast<cudaStream_t>(stream));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    rc = launch_scan(h, q_dev, s);
     if (rc) return rc;
-    return ngu_epi_append(h, q_dev, stream);
+    // one epilogue launch: rank sums -> running-mean update -> rewards -> log-only stats -> append
+    return launch_epilogue(h, PH_RANKSUMS | PH_FINISH | PH_APPEND | PH_LOGFUSE, nullptr, alpha_dev, r_int_dev,
+                           r_epi_dev, nullptr, q_dev, s);
 }
 
 int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host, float* r_int_host,

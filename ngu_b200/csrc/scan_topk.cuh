@@ -23,7 +23,13 @@
 //     the running k-th-best threshold is a warp-uniform register (WarpTopK).
 //   * work = B * ceil(N / TILE_ROWS) tiles, cut into equal contiguous chunks of
 //     `tiles_per_warp`; a warp that crosses an actor boundary flushes its list
-//     and starts a new one.  Partial lists go to partial[B][max_parts][k].
+//     and starts a new one.  Partial lists go to partial[B][max_parts][k]; the
+//     LAST warp to flush a given actor (per-actor arrival counter) merges that
+//     actor's partial lists in-kernel and writes the final k-NN (d^2, slot, dist),
+//     so no separate merge launch sits on the step's critical path.
+//   * programmatic dependent launch: the kernel lets its dependent (the epilogue
+//     kernel) get resident immediately and itself waits on its predecessor only
+//     right before the first TMA load (griddepcontrol).
 //
 // Arithmetic order (bit-exact with torch 2.11 CPU):
 //   diff = m - q ; s = diff*diff (separately rounded, no FMA);
@@ -47,9 +53,61 @@ struct ScanParams {
     int32_t tiles_per_actor; // ceil(N / TILE_ROWS)
     int32_t tiles_per_warp;  // chunk length
     int32_t max_parts;       // partial lists reserved per actor
-    int32_t pad0;
+    int32_t sqrt_dist;       // 1: dist = sqrt(d2) (reference), 0: dist = d2 (paper)
     int64_t total_tiles;     // B * tiles_per_actor
+    unsigned int* actor_arrivals;  // [B] zero between launches
+    float* topk_d2;          // [B][k]
+    int32_t* topk_idx;       // [B][k]
+    float* dist;             // [B][k]
 };
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Final k-NN of one actor from the warp-resident list.
+__device__ __forceinline__ void write_knn(const ScanParams& p, int actor, const WarpTopK& top, int lane) {
+    if (lane < p.k) {
+        const bool largest = p.largest != 0;
+        const float d2 = key_d2(top.lkey, largest);
+        const int64_t o = static_cast<int64_t>(actor) * p.k + lane;
+        p.topk_d2[o] = d2;
+        p.topk_idx[o] = key_slot(top.lkey);
+        p.dist[o] = p.sqrt_dist ? __fsqrt_rn(d2) : d2;   // episodic_novelty.py:52 .sqrt(), winners only
+    }
+}
+
+// Called by a whole warp when it has finished its share of `actor`.
+__device__ __forceinline__ void flush_actor(const ScanParams& p, int actor, int64_t gw, WarpTopK& top, int lane) {
+    const int64_t t0 = static_cast<int64_t>(actor) * p.tiles_per_actor;
+    const int first = static_cast<int>(t0 / p.tiles_per_warp);
+    const int last = static_cast<int>((t0 + p.tiles_per_actor - 1) / p.tiles_per_warp);
+    const int nparts = last - first + 1;
+    if (nparts == 1) {           // this warp scanned the whole actor
+        write_knn(p, actor, top, lane);
+        return;
+    }
+    const int k = p.k;
+    u64* base = p.partial + static_cast<int64_t>(actor) * p.max_parts * k;
+    if (lane < k) base[(gw - first) * k + lane] = top.lkey;
+    __threadfence();
+    __syncwarp();
+    unsigned prev = 0;
+    if (lane == 0) prev = atomicAdd(p.actor_arrivals + actor, 1u);
+    prev = __shfl_sync(kFull, prev, 0);
+    if (prev != static_cast<unsigned>(nparts - 1)) return;
+    // last arrival: every partial list of this actor is in L2
+    __threadfence();
+    if (lane == 0) p.actor_arrivals[actor] = 0;   // re-arm for the next launch
+    WarpTopK m;
+    m.reset();
+    const int nkeys = nparts * k;
+    for (int i0 = 0; i0 < nkeys; i0 += 32) {
+        const int i = i0 + lane;
+        const u64 key = i < nkeys ? __ldcg(base + i) : 0ull;
+        m.offer(key, lane, k);
+    }
+    write_knn(p, actor, m, lane);
+}
 
 // ---- PTX wrappers ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -75,12 +133,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// The memory stream is read exactly once per step and is ~8x the L2: tag it evict-first so
+// it does not flush the small hot data (queries, partial lists, running statistics, the
+// epilogue's inputs) out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0,
-                                            int32_t c1, uint32_t bar) {
+                                            int32_t c1, uint32_t bar, uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar), "l"(policy)
         : "memory");
 }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -149,6 +215,7 @@ __global__ void __launch_bounds__(WARPS * 32) scan_topk_kernel(const __grid_cons
     const uint32_t my_tiles = tiles0 + warp * STAGES * Cfg::kTileBytes;
     const uint32_t my_bars = bars0 + warp * STAGES * 8;
 
+    pdl_launch_dependents();   // the epilogue kernel may become resident now; it waits on us
     const int64_t gw = static_cast<int64_t>(blockIdx.x) * WARPS + warp;
     const int64_t t_begin = gw * p.tiles_per_warp;
     int64_t t_end = t_begin + p.tiles_per_warp;
@@ -162,6 +229,7 @@ __global__ void __launch_bounds__(WARPS * 32) scan_topk_kernel(const __grid_cons
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncwarp();
+    pdl_wait();   // predecessor (previous step's epilogue: append, readers of dist/topk) is complete
 
     const int tpa = p.tiles_per_actor;
     const int N = p.capacity;
@@ -169,6 +237,7 @@ __global__ void __launch_bounds__(WARPS * 32) scan_topk_kernel(const __grid_cons
     int ti = static_cast<int>(t_begin - static_cast<int64_t>(b) * tpa);  // tile index inside the actor
 
     // Prologue: fill the ring.  (Producer cursor runs STAGES tiles ahead.)
+    const uint64_t policy = l2_evict_first_policy();
     int pb = b, pti = ti;
     if (lane == 0) {
 #pragma unroll
@@ -177,7 +246,7 @@ __global__ void __launch_bounds__(WARPS * 32) scan_topk_kernel(const __grid_cons
                 const uint32_t bar = my_bars + 8 * s;
                 mbar_expect_tx(bar, Cfg::kTileBytes);
                 tma_load_2d(my_tiles + s * Cfg::kTileBytes, &tmap, 0,
-                            pb * N + pti * Cfg::kTileRows, bar);
+                            pb * N + pti * Cfg::kTileRows, bar, policy);
                 if (++pti == tpa) { pti = 0; ++pb; }
             }
         }
@@ -194,11 +263,7 @@ __global__ void __launch_bounds__(WARPS * 32) scan_topk_kernel(const __grid_cons
 
     for (int64_t t = t_begin; t < t_end; ++t) {
         if (b != cur) {
-            if (cur >= 0) {
-                const int first = static_cast<int>((static_cast<int64_t>(cur) * tpa) / p.tiles_per_warp);
-                if (lane < k)
-                    p.partial[(static_cast<int64_t>(cur) * p.max_parts + (gw - first)) * k + lane] = top.lkey;
-            }
+            if (cur >= 0) flush_actor(p, cur, gw, top, lane);
             cur = b;
             top.reset();
             const float4* qv = reinterpret_cast<const float4*>(p.q + static_cast<int64_t>(b) * 32);
@@ -222,7 +287,7 @@ __global__ void __launch_bounds__(WARPS * 32) scan_topk_kernel(const __grid_cons
         if (lane == 0 && t + STAGES < t_end) {
             const uint32_t bar = my_bars + 8 * stage;
             mbar_expect_tx(bar, Cfg::kTileBytes);
-            tma_load_2d(tile, &tmap, 0, pb * N + pti * Cfg::kTileRows, bar);
+            tma_load_2d(tile, &tmap, 0, pb * N + pti * Cfg::kTileRows, bar, policy);
             if (++pti == tpa) { pti = 0; ++pb; }
         }
 
@@ -237,11 +302,7 @@ __global__ void __launch_bounds__(WARPS * 32) scan_topk_kernel(const __grid_cons
         if (++ti == tpa) { ti = 0; ++b; }
     }
 
-    {
-        const int first = static_cast<int>((static_cast<int64_t>(cur) * tpa) / p.tiles_per_warp);
-        if (lane < k)
-            p.partial[(static_cast<int64_t>(cur) * p.max_parts + (gw - first)) * k + lane] = top.lkey;
-    }
+    flush_actor(p, cur, gw, top, lane);
 }
 
 }  // namespace ngu

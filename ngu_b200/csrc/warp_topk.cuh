@@ -44,26 +44,30 @@ struct WarpTopK {
 
     __device__ __forceinline__ void reset() { lkey = 0; thr = 0; }
 
-    // Offer one key per lane.  `k` is warp-uniform, 1..32.
+    // Offer one key per lane.  `k` is warp-uniform, 1..32.  The common case (nobody
+    // beats the k-th best) is 2 compares + 1 vote.  (The slow path stays inline: an
+    // out-of-line call would force the list registers through local memory.)
     __device__ __forceinline__ void offer(u64 key, int lane, int k) {
-        const bool cand = key > thr;
-        unsigned m = __ballot_sync(kFull, cand);
-        if (m == 0) return;
+        const unsigned m = __ballot_sync(kFull, key > thr);
+        if (m != 0) insert(key, m, lane, k);
+    }
+
+    __device__ __forceinline__ void insert(u64 key, unsigned m, int lane, int k) {
         if (__popc(m) > 6) {
-            merge_batch(cand ? key : 0ull, lane, k);
-        } else {
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const u64 c = __shfl_sync(kFull, key, src);
-                if (c > thr) {  // warp-uniform: thr may have risen since the ballot
-                    const unsigned better = __ballot_sync(kFull, lkey > c);  // prefix mask
-                    const int pos = __popc(better);
-                    const u64 up = __shfl_up_sync(kFull, lkey, 1);
-                    if (lane == pos) lkey = c;
-                    else if (lane > pos) lkey = up;
-                    thr = __shfl_sync(kFull, lkey, k - 1);
-                }
+            merge_batch(((m >> lane) & 1u) ? key : 0ull, lane, k);
+            return;
+        }
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const u64 c = __shfl_sync(kFull, key, src);
+            if (c > thr) {  // warp-uniform: thr may have risen since the ballot
+                const unsigned better = __ballot_sync(kFull, lkey > c);  // prefix mask
+                const int pos = __popc(better);
+                const u64 up = __shfl_up_sync(kFull, lkey, 1);
+                if (lane == pos) lkey = c;
+                else if (lane > pos) lkey = up;
+                thr = __shfl_sync(kFull, lkey, k - 1);
             }
         }
     }
@@ -71,9 +75,9 @@ struct WarpTopK {
     // Full-width path: sort the batch descending (bitonic network over lanes),
     // then keep the 32 largest of (list U batch) with one bitonic merge.
     __device__ __forceinline__ void merge_batch(u64 x, int lane, int k) {
-#pragma unroll
+#pragma unroll 1
         for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
+#pragma unroll 1
             for (int j = size >> 1; j > 0; j >>= 1) {
                 const u64 o = __shfl_xor_sync(kFull, x, j);
                 const bool desc_block = (lane & size) == 0;
@@ -84,7 +88,7 @@ struct WarpTopK {
         // x descending.  max(list[i], x[31-i]) is bitonic and holds the top 32.
         const u64 y = __shfl_sync(kFull, x, 31 - lane);
         u64 z = umax64(lkey, y);
-#pragma unroll
+#pragma unroll 1
         for (int j = 16; j > 0; j >>= 1) {
             const u64 o = __shfl_xor_sync(kFull, z, j);
             z = ((lane & j) == 0) ? umax64(z, o) : umin64(z, o);

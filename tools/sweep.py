@@ -1,5 +1,6 @@
 """Scratch: time the scan variants on the GPU box (not part of the product)."""
-import sys, json
+import sys, json, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from ngu_b200.engine import EpisodicEngine
 
