@@ -194,15 +194,12 @@ def run_gpu_arm(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # warm-up: W steps, then keep stepping (untimed) until the clocks have had time to ramp
-    for i in range(args.warmup):
+    # warm-up: W steps, then a fixed number of extra untimed steps (~0.25 s) so the SM clocks have
+    # ramped before the timed region; the count is fixed (not time-based) so that every rank issues
+    # the same sequence of collectives
+    for i in range(args.warmup + 1500):
         sh.step(qs[i % NQ], al[i % NQ])
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    i = 0
-    while time.perf_counter() - t0 < 0.25:
-        sh.step(qs[i % NQ], al[i % NQ]); i += 1
-        if i % 64 == 0:
+        if i % 128 == 127:
             torch.cuda.synchronize()
     barrier()
 

@@ -87,6 +87,7 @@ typedef struct ngu_epi_state {
     double intr_mean, intr_var, intr_count;
     int64_t cursor;
     int64_t steps;              /* finished steps since create / set_state */
+    int64_t exchange_timeouts;  /* read-only: p2p exchange rounds that timed out waiting for a peer (0 = healthy) */
 } ngu_epi_state;
 
 /* Number of doubles exchanged between shards per step:
@@ -175,6 +176,17 @@ int ngu_epi_set_state(ngu_epi* h, const ngu_epi_state* in); /* synchronous */
  * float[capacity][n_actors][32] on the host (tests, checkpoints).  Synchronous. */
 int ngu_epi_load_memory_host(ngu_epi* h, const float* slot_major_host);
 int ngu_epi_dump_memory_host(ngu_epi* h, float* slot_major_host);
+
+/* Multi-GPU, one process per GPU: replace the caller's all-reduce by an exchange over NVLink peer
+ * memory fused into the finish kernel (what MPI.Allreduce does at mpi_util.py:17).
+ *   1. every rank:  ngu_epi_p2p_export(h, handle [64 bytes out], world)
+ *   2. all-gather the 64-byte handles in rank order (any transport)
+ *   3. every rank:  ngu_epi_p2p_connect(h, rank, world, handles [world*64 bytes])
+ * Afterwards ngu_epi_step / ngu_epi_step_host sum the rank sums (and the log-only sums) over all
+ * ranks inside the epilogue kernel; all ranks must call them in lockstep.  Ranks must sit on
+ * DISTINCT GPUs (the kernel spins on flags written by the peers). */
+int ngu_epi_p2p_export(ngu_epi* h, void* ipc_handle_out, int32_t world);
+int ngu_epi_p2p_connect(ngu_epi* h, int32_t rank, int32_t world, const void* ipc_handles);
 
 /* Introspection for bench.py / DESIGN.md: kernels launched by the handle so far,
  * and the scan launch geometry {grid, block, dyn_smem, tiles_per_warp, stages, tile_rows}. */

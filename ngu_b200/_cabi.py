@@ -32,7 +32,7 @@ class NguEpiState(C.Structure):
         ("ed_mean", C.c_double * MAX_K), ("ed_var", C.c_double * MAX_K), ("ed_count", C.c_double),
         ("epi_mean", C.c_double), ("epi_var", C.c_double), ("epi_count", C.c_double),
         ("intr_mean", C.c_double), ("intr_var", C.c_double), ("intr_count", C.c_double),
-        ("cursor", C.c_int64), ("steps", C.c_int64),
+        ("cursor", C.c_int64), ("steps", C.c_int64), ("exchange_timeouts", C.c_int64),
     ]
 
 
@@ -58,6 +58,8 @@ SYMBOLS = {
     "ngu_epi_set_state": (C.c_int, [_P, C.POINTER(NguEpiState)]),
     "ngu_epi_load_memory_host": (C.c_int, [_P, _P]),
     "ngu_epi_dump_memory_host": (C.c_int, [_P, _P]),
+    "ngu_epi_p2p_export": (C.c_int, [_P, _P, C.c_int32]),
+    "ngu_epi_p2p_connect": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "ngu_epi_launch_count": (C.c_int64, [_P]),
     "ngu_epi_scan_geometry": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "ngu_epi_scan_timing_begin": (C.c_int, [_P, C.c_int32]),

@@ -13,6 +13,7 @@
 #pragma once
 #include <cstdint>
 
+#include "p2p_exchange.cuh"
 #include "warp_topk.cuh"
 
 namespace ngu {
@@ -26,7 +27,7 @@ struct DevState {
     double intr_mean, intr_var, intr_count;
     long long steps;     // the 8 words from ed_count to steps are staged together by the epilogue
     long long cursor;
-    long long pad;
+    long long exchange_timeouts;   // p2p exchange rounds that gave up waiting for a peer (must stay 0)
 };
 
 struct EpiConsts {
@@ -108,7 +109,9 @@ __device__ __forceinline__ float np_pairwise_sum8(const float* v, int stride, co
 //             product (intrinsic_novelty.py:26-31), log-only batch sums
 //   APPEND    insert_state (episodic_novelty.py:86-89)
 // ---------------------------------------------------------------------------
-enum : int { PH_RANKSUMS = 1, PH_FINISH = 2, PH_APPEND = 4, PH_LOGFUSE = 8 };
+//   EXCHANGE  (multi-GPU, p2p mode) sum the rank sums - and, after the rewards, the log-only
+//             sums - over all shards through NVLink peer stores (p2p_exchange.cuh)
+enum : int { PH_RANKSUMS = 1, PH_FINISH = 2, PH_APPEND = 4, PH_LOGFUSE = 8, PH_EXCHANGE = 16 };
 
 struct EpilogueParams {
     const float* dist;        // [B][k]  sqrt(d2) (reference) or d2 (paper), written by the scan kernel
@@ -126,6 +129,7 @@ struct EpilogueParams {
     int32_t phases;
     int32_t stage_q;          // 1: q fits the dynamic shared memory of this launch
     int32_t pad;
+    P2PView p2p;              // used when phases & PH_EXCHANGE
 };
 
 // Chan/Welford merge of (mean, var, count) with a batch (mpi_util.py:59-73), all f64.
@@ -174,6 +178,7 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
     __shared__ float mean32[32];
     __shared__ double red[4][THREADS / 32];
     __shared__ long long s_cursor;
+    __shared__ double s_log[8];
     __shared__ int2 s_plan[64];
     __shared__ float s_stack[256][kPlanMaxDepth + 1];   // value stacks of the rank-sum threads (padded)
     extern __shared__ float s_dyn[];
@@ -250,6 +255,13 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
         if (threadIdx.x < 2 * k + 1) p.rank_sums[threadIdx.x] = s_sums[threadIdx.x];
     }
 
+    const bool exchange = (p.phases & PH_EXCHANGE) != 0;
+    const unsigned long long step_id = exchange ? static_cast<unsigned long long>(__double_as_longlong(s_scal[7])) : 0ull;
+    if (exchange) {   // round 1: global rank sums (mpi_util.py:17)
+        if (!p2p_allreduce<THREADS>(p.p2p, s_sums, 2 * k + 1, 0, kSlotFlag1, step_id) && threadIdx.x == 0)
+            atomicAdd(reinterpret_cast<unsigned long long*>(&st->exchange_timeouts), 1ull);
+    }
+
     if (finish) {
         if (threadIdx.x < k) {
             const int j = threadIdx.x;
@@ -316,20 +328,27 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
             __syncthreads();
             if (threadIdx.x < 32) {
                 // lanes 0..15 hold one warp partial each; 4 quantities reduced by shuffles
-                double ls[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     double v = threadIdx.x < THREADS / 32 ? red[q][threadIdx.x] : 0.0;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-                    ls[q] = v;
+                    if (threadIdx.x == 0) s_log[q] = v;
                 }
-                const double n = static_cast<double>(B);
-                if (p.log_sums && threadIdx.x < 5) p.log_sums[threadIdx.x] = threadIdx.x < 4 ? ls[threadIdx.x] : n;
-                if ((p.phases & PH_LOGFUSE) && threadIdx.x < 2) {
+                if (threadIdx.x == 0) s_log[4] = static_cast<double>(B);
+            }
+            __syncthreads();
+            if (p.log_sums && threadIdx.x < 5) p.log_sums[threadIdx.x] = s_log[threadIdx.x];
+            if (p.phases & PH_LOGFUSE) {
+                if (exchange) {   // round 2: global log-only sums (episodic_novelty.py:82, intrinsic_novelty.py:32)
+                    if (!p2p_allreduce<THREADS>(p.p2p, s_log, 5, kSlotLog, kSlotFlag2, step_id) && threadIdx.x == 0)
+                        atomicAdd(reinterpret_cast<unsigned long long*>(&st->exchange_timeouts), 1ull);
+                }
+                if (threadIdx.x < 2) {
                     // lane 0: epi_novel_rms, lane 1: intrinsic_novel_rms (staged in s_scal[1..6])
                     const int o = 2 * threadIdx.x;
-                    const double m = f64_div(ls[o], n), v = fmax(f64_div(ls[o + 1], n) - m * m, 0.0);
+                    const double n = s_log[4];
+                    const double m = f64_div(s_log[o], n), v = fmax(f64_div(s_log[o + 1], n) - m * m, 0.0);
                     double* sc = s_scal + 1 + 3 * threadIdx.x;
                     rms_merge(&sc[0], &sc[1], &sc[2], m, v, n);
                     for (int q = 0; q < 3; ++q) (&st->ed_count)[1 + 3 * threadIdx.x + q] = sc[q];

@@ -97,16 +97,21 @@ struct ngu_epi {
     unsigned int* actor_arrivals = nullptr;  // [B] per-actor flush counter of the scan kernel
     int2* plan_dev = nullptr;        // pairwise-sum plan for n = B (epilogue rank sums)
     int plan_len = 0;
+    // p2p rank-sum exchange (multi-GPU): local inbox + IPC-mapped peer inboxes
+    double* inbox = nullptr;
+    P2PView p2p{};
+    bool p2p_connected = false;
     DevState* state = nullptr;
     bool use_pdl = true;
     int debug_phase_mask = ~0;       // NGU_EPI_DEBUG_PHASES: experiments only (tools/sweep.py)
     // staging for the *_host entry points
     cudaStream_t own_stream = nullptr;
-    float* q_stage_dev = nullptr;    // [B][32]
-    float* a_stage_dev = nullptr;    // [B]
-    float* r_stage_dev = nullptr;    // [2][B]
+    float* q_stage_dev = nullptr;    // [B][32] followed by alpha [B]: one H2D copy per step
+    float* a_stage_dev = nullptr;    // = q_stage_dev + B*32
     uint8_t* done_stage_dev = nullptr;
-    float* pinned = nullptr;         // [B*32 + B + 2B] floats + B bytes
+    float* pinned = nullptr;         // host: [B*32 q][B alpha] floats + B done bytes
+    float* r_mapped = nullptr;       // host, mapped: [2][B] rewards written by the epilogue over PCIe (zero-copy)
+    float* r_mapped_dev = nullptr;   // device alias of r_mapped
     // launch geometry
     Variant var{};
     CUtensorMap tmap{};
@@ -276,11 +281,12 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
         CREATE_TRY(cudaMemcpy(h->plan_dev, plan.data(), plan.size() * sizeof(int2), cudaMemcpyHostToDevice));
     }
     CREATE_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    CREATE_TRY(cudaMalloc(&h->q_stage_dev, static_cast<size_t>(B) * 32 * sizeof(float)));
-    CREATE_TRY(cudaMalloc(&h->a_stage_dev, static_cast<size_t>(B) * sizeof(float)));
-    CREATE_TRY(cudaMalloc(&h->r_stage_dev, static_cast<size_t>(B) * 2 * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&h->q_stage_dev, static_cast<size_t>(B) * 33 * sizeof(float)));
+    h->a_stage_dev = h->q_stage_dev + static_cast<size_t>(B) * 32;
     CREATE_TRY(cudaMalloc(&h->done_stage_dev, static_cast<size_t>(B)));
-    CREATE_TRY(cudaMallocHost(&h->pinned, static_cast<size_t>(B) * (32 + 1 + 2) * sizeof(float) + B));
+    CREATE_TRY(cudaMallocHost(&h->pinned, static_cast<size_t>(B) * 33 * sizeof(float) + B));
+    CREATE_TRY(cudaHostAlloc(&h->r_mapped, static_cast<size_t>(B) * 2 * sizeof(float), cudaHostAllocMapped));
+    CREATE_TRY(cudaHostGetDevicePointer(&h->r_mapped_dev, h->r_mapped, 0));
 #undef CREATE_TRY
 
     EpiConsts& c = h->consts;
@@ -307,11 +313,16 @@ void ngu_epi_destroy(ngu_epi* h) {
     if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
     for (cudaEvent_t e : h->t_beg) cudaEventDestroy(e);
     for (cudaEvent_t e : h->t_end) cudaEventDestroy(e);
+    if (h->p2p_connected)
+        for (int g = 0; g < h->p2p.world; ++g)
+            if (g != h->p2p.rank && h->p2p.peer[g]) cudaIpcCloseMemHandle(h->p2p.peer[g]);
+    cudaFree(h->inbox);
     if (h->owns_memory) cudaFree(h->memory);
     cudaFree(h->partial); cudaFree(h->topk_d2); cudaFree(h->topk_idx); cudaFree(h->dist);
     cudaFree(h->rank_sums); cudaFree(h->log_sums); cudaFree(h->state); cudaFree(h->actor_arrivals); cudaFree(h->plan_dev);
-    cudaFree(h->q_stage_dev); cudaFree(h->a_stage_dev); cudaFree(h->r_stage_dev); cudaFree(h->done_stage_dev);
+    cudaFree(h->q_stage_dev); cudaFree(h->done_stage_dev);
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->r_mapped) cudaFreeHost(h->r_mapped);
     delete h;
 }
 
@@ -363,6 +374,10 @@ static int launch_epilogue(ngu_epi* h, int phases, const double* sums_in, const 
     ep.dist = h->dist; ep.rank_sums = h->rank_sums; ep.sums_in = sums_in; ep.alpha = alpha;
     ep.r_int = r_int; ep.r_epi = r_epi; ep.log_sums = log_sums; ep.q = q; ep.memory = h->memory;
     ep.state = h->state; ep.phases = phases & h->debug_phase_mask;
+    if (h->p2p_connected && (phases & PH_FINISH) && (phases & PH_RANKSUMS)) {   // fused single-launch step only
+        ep.phases |= PH_EXCHANGE;
+        ep.p2p = h->p2p;
+    }
     ep.plan = h->plan_dev; ep.plan_len = h->plan_len;
     // dynamic smem: [dist B*k][alpha B][q B*32] when it all fits, else without q
     ep.stage_q = epilogue_smem_bytes(h->cfg.n_actors, h->cfg.k, true) <= kEpilogueStageBytes ? 1 : 0;
@@ -457,23 +472,20 @@ int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host, 
     if (!h || !q_host || !r_int_host) return fail(h, NGU_EINVAL, "null argument");
     int rc = bind_device(h);
     if (rc) return rc;
-    const int B = h->cfg.n_actors;
+    const size_t B = h->cfg.n_actors;
     cudaStream_t s = h->own_stream;
-    float* pq = h->pinned;
-    float* pa = pq + static_cast<size_t>(B) * 32;
-    float* pr = pa + B;
-    std::memcpy(pq, q_host, static_cast<size_t>(B) * 32 * sizeof(float));
-    CU_TRY(h, cudaMemcpyAsync(h->q_stage_dev, pq, static_cast<size_t>(B) * 32 * sizeof(float), cudaMemcpyHostToDevice, s));
-    if (alpha_host) {
-        std::memcpy(pa, alpha_host, static_cast<size_t>(B) * sizeof(float));
-        CU_TRY(h, cudaMemcpyAsync(h->a_stage_dev, pa, static_cast<size_t>(B) * sizeof(float), cudaMemcpyHostToDevice, s));
-    }
-    rc = ngu_epi_step(h, h->q_stage_dev, alpha_host ? h->a_stage_dev : nullptr, h->r_stage_dev, h->r_stage_dev + B, s);
+    // one pinned H2D copy carries the step's controllable states and (optionally) the modulators;
+    // the rewards come back zero-copy: the epilogue kernel writes them straight into mapped host memory
+    std::memcpy(h->pinned, q_host, B * 32 * sizeof(float));
+    if (alpha_host) std::memcpy(h->pinned + B * 32, alpha_host, B * sizeof(float));
+    CU_TRY(h, cudaMemcpyAsync(h->q_stage_dev, h->pinned, B * (alpha_host ? 33 : 32) * sizeof(float),
+                              cudaMemcpyHostToDevice, s));
+    rc = ngu_epi_step(h, h->q_stage_dev, alpha_host ? h->a_stage_dev : nullptr, h->r_mapped_dev,
+                      h->r_mapped_dev + B, s);
     if (rc) return rc;
-    CU_TRY(h, cudaMemcpyAsync(pr, h->r_stage_dev, static_cast<size_t>(B) * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
     CU_TRY(h, cudaStreamSynchronize(s));
-    std::memcpy(r_int_host, pr, static_cast<size_t>(B) * sizeof(float));
-    if (r_epi_host) std::memcpy(r_epi_host, pr + B, static_cast<size_t>(B) * sizeof(float));
+    std::memcpy(r_int_host, h->r_mapped, B * sizeof(float));
+    if (r_epi_host) std::memcpy(r_epi_host, h->r_mapped + B, B * sizeof(float));
     return NGU_OK;
 }
 
@@ -485,7 +497,7 @@ int ngu_epi_reset_host(ngu_epi* h, const uint8_t* done_host) {
     bool any = false;
     for (int b = 0; b < B; ++b) any |= done_host[b] != 0;
     if (!any) return NGU_OK;   // nothing to zero: skip the launch (the common step)
-    uint8_t* pd = reinterpret_cast<uint8_t*>(h->pinned + static_cast<size_t>(B) * 35);
+    uint8_t* pd = reinterpret_cast<uint8_t*>(h->pinned + static_cast<size_t>(B) * 33);
     std::memcpy(pd, done_host, B);
     CU_TRY(h, cudaMemcpyAsync(h->done_stage_dev, pd, B, cudaMemcpyHostToDevice, h->own_stream));
     rc = ngu_epi_reset(h, h->done_stage_dev, h->own_stream);
@@ -517,7 +529,7 @@ int ngu_epi_get_state(ngu_epi* h, ngu_epi_state* out) {
     out->ed_count = d.ed_count;
     out->epi_mean = d.epi_mean; out->epi_var = d.epi_var; out->epi_count = d.epi_count;
     out->intr_mean = d.intr_mean; out->intr_var = d.intr_var; out->intr_count = d.intr_count;
-    out->cursor = d.cursor; out->steps = d.steps;
+    out->cursor = d.cursor; out->steps = d.steps; out->exchange_timeouts = d.exchange_timeouts;
     return NGU_OK;
 }
 
@@ -572,6 +584,44 @@ int ngu_epi_load_memory_host(ngu_epi* h, const float* slot_major_host) {
 int ngu_epi_dump_memory_host(ngu_epi* h, float* slot_major_host) {
     if (!h || !slot_major_host) return fail(h, NGU_EINVAL, "null argument");
     return transpose_copy(h, nullptr, slot_major_host);
+}
+
+int ngu_epi_p2p_export(ngu_epi* h, void* ipc_handle_out, int32_t world) {
+    if (!h || !ipc_handle_out) return fail(h, NGU_EINVAL, "null argument");
+    if (world < 2 || world > kMaxWorld) return fail(h, NGU_EINVAL, fmt("world must be 2..%d", kMaxWorld));
+    int rc = bind_device(h);
+    if (rc) return rc;
+    if (!h->inbox) {
+        const size_t bytes = static_cast<size_t>(2) * world * kSlotDoubles * sizeof(double);
+        CU_TRY(h, cudaMalloc(&h->inbox, bytes));
+        CU_TRY(h, cudaMemset(h->inbox, 0, bytes));
+        CU_TRY(h, cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t hd;
+    CU_TRY(h, cudaIpcGetMemHandle(&hd, h->inbox));
+    static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(ipc_handle_out, &hd, sizeof hd);
+    return NGU_OK;
+}
+
+int ngu_epi_p2p_connect(ngu_epi* h, int32_t rank, int32_t world, const void* ipc_handles) {
+    if (!h || !ipc_handles) return fail(h, NGU_EINVAL, "null argument");
+    if (!h->inbox) return fail(h, NGU_ESTATE, "call ngu_epi_p2p_export first");
+    if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world) return fail(h, NGU_EINVAL, "bad rank/world");
+    int rc = bind_device(h);
+    if (rc) return rc;
+    h->p2p = P2PView{};
+    h->p2p.inbox = h->inbox; h->p2p.rank = rank; h->p2p.world = world;
+    for (int g = 0; g < world; ++g) {
+        if (g == rank) { h->p2p.peer[g] = h->inbox; continue; }
+        cudaIpcMemHandle_t hd;
+        std::memcpy(&hd, static_cast<const char*>(ipc_handles) + 64 * g, sizeof hd);
+        void* ptr = nullptr;
+        CU_TRY(h, cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+        h->p2p.peer[g] = static_cast<double*>(ptr);
+    }
+    h->p2p_connected = true;
+    return NGU_OK;
 }
 
 int64_t ngu_epi_launch_count(const ngu_epi* h) { return h ? h->launches : 0; }

@@ -143,16 +143,22 @@ class EpisodicEngine:
 
     # ---- host-buffer path (what the drop-in calls with CPU tensors) ---------------
     def step_host(self, q: np.ndarray, alpha: np.ndarray | None = None):
-        q = np.ascontiguousarray(q, dtype=np.float32)
+        """ngu_epi_step_host: host float32 arrays in, host float32 rewards (r_int, r_epi) out, synchronous."""
+        if not (isinstance(q, np.ndarray) and q.dtype == np.float32 and q.flags.c_contiguous):
+            q = np.ascontiguousarray(q, dtype=np.float32)
         if q.shape != (self.n_actors, _cabi.DIM):
             raise ValueError(f"controllable state must be ({self.n_actors}, {_cabi.DIM}), got {q.shape}")
-        a = None if alpha is None else np.ascontiguousarray(alpha, dtype=np.float32)
-        r_int = np.empty(self.n_actors, np.float32)
-        r_epi = np.empty(self.n_actors, np.float32)
-        check(self._lib.ngu_epi_step_host(self._h, q.ctypes.data_as(C.c_void_p),
-                                          None if a is None else a.ctypes.data_as(C.c_void_p),
-                                          r_int.ctypes.data_as(C.c_void_p), r_epi.ctypes.data_as(C.c_void_p)), self._h)
-        return r_int, r_epi
+        a_ptr = None
+        if alpha is not None:
+            if not (isinstance(alpha, np.ndarray) and alpha.dtype == np.float32 and alpha.flags.c_contiguous):
+                alpha = np.ascontiguousarray(alpha, dtype=np.float32)
+            if alpha.shape != (self.n_actors,):
+                raise ValueError(f"alpha must be ({self.n_actors},), got {alpha.shape}")
+            a_ptr = alpha.ctypes.data
+        out = np.empty((2, self.n_actors), np.float32)
+        check(self._lib.ngu_epi_step_host(self._h, q.ctypes.data, a_ptr, out.ctypes.data,
+                                          out.ctypes.data + 4 * self.n_actors), self._h)
+        return out[0], out[1]
 
     def reset_host(self, done: np.ndarray):
         d = np.ascontiguousarray(done, dtype=np.uint8)
@@ -175,7 +181,7 @@ class EpisodicEngine:
         return dict(ed_mean=np.array(s.ed_mean[:k]), ed_var=np.array(s.ed_var[:k]), ed_count=s.ed_count,
                     epi_mean=s.epi_mean, epi_var=s.epi_var, epi_count=s.epi_count,
                     intr_mean=s.intr_mean, intr_var=s.intr_var, intr_count=s.intr_count,
-                    cursor=int(s.cursor), steps=int(s.steps))
+                    cursor=int(s.cursor), steps=int(s.steps), exchange_timeouts=int(s.exchange_timeouts))
 
     def set_state(self, st: dict):
         s = NguEpiState()
@@ -200,6 +206,17 @@ class EpisodicEngine:
         out = np.empty((self.capacity, self.n_actors, _cabi.DIM), np.float32)
         check(self._lib.ngu_epi_dump_memory_host(self._h, out.ctypes.data_as(C.c_void_p)), self._h)
         return out
+
+    # ---- multi-GPU p2p exchange ------------------------------------------------------------
+    def p2p_export(self, world: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(self._lib.ngu_epi_p2p_export(self._h, buf, int(world)), self._h)
+        return buf.raw
+
+    def p2p_connect(self, rank: int, world: int, handles: list):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        check(self._lib.ngu_epi_p2p_connect(self._h, int(rank), int(world), blob), self._h)
 
     @property
     def launch_count(self) -> int:

@@ -39,7 +39,7 @@ class ShardedEpisodicEngine:
     """This rank's shard of a `global_actors`-actor episodic memory."""
 
     def __init__(self, global_actors, capacity, group=None, device=None, track_log_stats=True,
-                 engine_factory=EpisodicEngine, **engine_kwargs):
+                 engine_factory=EpisodicEngine, exchange="auto", **engine_kwargs):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -54,6 +54,18 @@ class ShardedEpisodicEngine:
         k = self.engine.k
         self._sums = torch.zeros(2 * k + 1, dtype=torch.float64, device=self.engine.device)
         self._log = torch.zeros(5, dtype=torch.float64, device=self.engine.device)
+        # exchange transport: "p2p" = NVLink peer stores fused into the finish kernel (one process per
+        # GPU, distinct GPUs), "collective" = torch.distributed all-reduce between scan and finish
+        if exchange == "auto":
+            exchange = "p2p" if (self.world > 1 and dist.get_backend(group) == "nccl"
+                                 and hasattr(self.engine, "p2p_export")) else "collective"
+        self.exchange = exchange if self.world > 1 else "none"
+        if self.exchange == "p2p":
+            mine = self.engine.p2p_export(self.world)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine, group=group)
+            self.engine.p2p_connect(self.rank, self.world, handles)
+            dist.barrier(group=group)
 
     def local_slice(self, x):
         return x[self.lo:self.hi]
@@ -61,8 +73,8 @@ class ShardedEpisodicEngine:
     def step(self, q_local: torch.Tensor, alpha_local: torch.Tensor | None = None):
         """One hot-path step for this shard; returns device tensors (r_int, r_epi) of the local actors."""
         eng = self.engine
-        if self.world == 1:
-            return eng.step(q_local, alpha_local)
+        if self.world == 1 or self.exchange == "p2p":
+            return eng.step(q_local, alpha_local)      # p2p: the exchange happens inside the epilogue kernel
         eng.scan(q_local)
         self._sums.copy_(eng.rank_sums)
         exchange_sum(self._sums, self.group)                       # mpi_util.py:17

@@ -20,7 +20,7 @@ def lib():
 def test_exports_every_header_symbol(lib):
     from ngu_b200 import _cabi
     header = open(os.path.join(ROOT, "include", "ngu_epi.h")).read()
-    declared = set(re.findall(r"\b(ngu_epi_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(ngu_epi_[a-z0-9_]+)\s*\(", header))
     assert declared, "no declarations parsed"
     assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
     for name in declared:
@@ -31,7 +31,7 @@ def test_exports_every_header_symbol(lib):
 def test_struct_layout_matches_header():
     from ngu_b200 import _cabi
     assert C.sizeof(_cabi.NguEpiCfg) == 64
-    assert C.sizeof(_cabi.NguEpiState) == 8 * (32 + 32 + 1 + 6) + 16
+    assert C.sizeof(_cabi.NguEpiState) == 8 * (32 + 32 + 1 + 6) + 24
 
 
 def test_create_rejects_bad_config_and_missing_gpu(lib):

@@ -1,0 +1,108 @@
+"""Full-size checks at BASELINE.json's sizes (256 actors x 30 000 slots, and 1 x 30 000) through
+size-independent properties plus the plain-C oracle on a subset of actors."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_256x30k_properties_and_c_oracle_subset(cuda_device):
+    from ngu_b200.engine import EpisodicEngine
+    from oracle import c_oracle
+    from oracle.episodic_oracle import EpisodicOracle
+    B, N, k = 256, 30000, 10
+    eng = EpisodicEngine(B, N, k=k, device=0)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    eng._memory.normal_(generator=g)
+    # plant: actor 3 gets far outliers at known slots (the farthest-k must find exactly these),
+    # actor 5 gets exact duplicates of one row at many slots (tie rule: lowest slots win)
+    far = [29999, 17, 12345, 4, 20000, 9999, 1, 28000, 15000, 77]
+    for r, s in enumerate(far):
+        eng._memory[3, s] = 100.0 + r
+    dup_slots = list(range(1000, 30000, 997))
+    eng._memory[5, dup_slots] = 50.0
+    q = torch.randn(B, 32, device="cuda", generator=g)
+    mem_before = eng._memory.clone()
+    r_int, r_epi = eng.step(q, None)
+    d2, idx = eng.topk()
+    # property 1: planted outliers, ordered by distance (largest offset farthest)
+    assert idx[3].tolist() == far[::-1]
+    # property 2: ties -> lowest slots, in ascending slot order
+    assert idx[5].tolist() == dup_slots[:k]
+    assert len(set(d2[5].tolist())) == 1
+    # property 3: values descending, slots in range, bit-exact d2 recomputed on the host for the winners
+    assert (np.diff(d2, axis=1) <= 0).all() and (idx >= 0).all() and (idx < N).all()
+    from oracle.episodic_oracle import d2_lane8
+    memc = mem_before.cpu().numpy()
+    rows = np.take_along_axis(memc, idx[:, :, None].astype(np.int64), axis=1)      # [B,k,32]
+    chk = d2_lane8(rows, q.cpu().numpy()[:, None, :])
+    assert np.array_equal(chk.view(np.uint32), d2.view(np.uint32))
+    # property 4: append went to slot 0 for every actor, nothing else changed; cursor advanced
+    assert torch.equal(eng._memory[:, 0], q)
+    assert torch.equal(eng._memory[:, 1:], mem_before[:, 1:])
+    assert eng.get_state()["cursor"] == 1
+    # oracle (plain C scan) on 8 whole actors
+    sub = [0, 3, 5, 100, 101, 200, 254, 255]
+    mem_sub = np.ascontiguousarray(memc[sub].transpose(1, 0, 2))
+    oi, od = c_oracle.scan_topk(mem_sub, q.cpu().numpy()[sub], k, True)
+    assert np.array_equal(oi.T, idx[sub]) and np.array_equal(od.T.view(np.uint32), d2[sub].view(np.uint32))
+    # rewards: closed form from the engine's own top-k through the numpy oracle epilogue
+    orc = EpisodicOracle(B, 16, k=k)
+    want = orc.reward_from_topk(d2.T.copy(), None)
+    rel = np.abs(r_int.cpu().numpy() - want) / np.abs(want)
+    assert rel.max() <= 1e-5
+    # property 5: reset zeroes exactly the done actors
+    done = torch.zeros(B, dtype=torch.bool)
+    done[[3, 200]] = True
+    eng.reset(done)
+    torch.cuda.synchronize()
+    assert not eng._memory[3].any() and not eng._memory[200].any()
+    assert torch.equal(eng._memory[4], mem_before[4].index_put((torch.tensor([0], device="cuda"),), q[4:5]))
+    eng.close()
+
+
+def test_idempotent_rescan_and_single_actor_30k(cuda_device):
+    """Scanning twice without an append gives identical k-NN (the scan has no side effects on the memory)."""
+    from ngu_b200.engine import EpisodicEngine
+    from oracle import c_oracle
+    B, N, k = 1, 30000, 10
+    eng = EpisodicEngine(B, N, k=k, device=0)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    eng._memory.normal_(generator=g)
+    q = torch.randn(B, 32, device="cuda", generator=g)
+    eng.scan(q)
+    a = eng.topk()
+    eng.scan(q)
+    b = eng.topk()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    mem = np.ascontiguousarray(eng._memory.cpu().numpy().transpose(1, 0, 2))
+    oi, od = c_oracle.scan_topk(mem, q.cpu().numpy(), k, True)
+    assert np.array_equal(oi.T, a[1]) and np.array_equal(od.T.view(np.uint32), a[0].view(np.uint32))
+    eng.close()
+
+
+def test_long_trajectory_64x5000_vs_oracle(cuda_device):
+    """BASELINE configs[1] shape: 64 actors x 5 000 slots, 25 steps with resets, against the C-scan oracle."""
+    from ngu_b200.engine import EpisodicEngine
+    from oracle.episodic_oracle import EpisodicOracle
+    B, N, k = 64, 5000, 10
+    rng = np.random.default_rng(5)
+    mem0 = rng.standard_normal((N, B, 32), dtype=np.float32)
+    orc = EpisodicOracle(B, N, k=k, use_c_scan=True)
+    orc.memory[...] = mem0
+    eng = EpisodicEngine(B, N, k=k, device=0)
+    eng.load_memory(mem0)
+    for t in range(25):
+        q = rng.standard_normal((B, 32), dtype=np.float32)
+        alpha = (1 + 2 * rng.standard_normal(B)).astype(np.float32)
+        want = orc.step(q, alpha)
+        r_int, _ = eng.step_host(q, alpha)
+        d2, idx = eng.topk()
+        assert np.array_equal(idx.T, want["idx"])
+        assert (np.abs(r_int - want["reward"]) / np.abs(want["reward"])).max() <= 1e-5
+        done = rng.random(B) < 0.05
+        orc.reset(done)
+        eng.reset_host(done)
+    assert np.array_equal(eng.dump_memory(), orc.memory)
+    eng.close()
