@@ -262,7 +262,9 @@ def run_gpu_arm(args, rank, world, local_rank):
                        "capacity": N, "k": K_NEIGHBORS, "mode": "reference", "parallelism": f"actor-shard x{world}",
                        "l2": f"working set {B * N * 128 / 1e6:.0f} MB per GPU vs 126 MB L2 (inputs larger than L2)"
                              if B * N * 128 > 2 * 126e6 else "working set fits L2: cache-resident, flagged",
-                       "exchange": "none" if world == 1 else "21-double rank-sum all-reduce (NCCL) per step",
+                       "exchange": "none" if world == 1 else (
+                           "21-double rank sums + 5 log-only sums per step, NVLink peer stores fused into the finish kernel"
+                           if sh.exchange == "p2p" else "21-double rank-sum all-reduce (torch.distributed) per step"),
                        "scan_geometry": geo},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 32 * 4 + B * 4,
                     "d2h_bytes_per_step": 2 * B * 4 if world == 1 else B * 4},

@@ -35,7 +35,8 @@ def launches(path, tag, note):
     agg = collections.OrderedDict()
     for row in csv.DictReader(lines):
         agg.setdefault(row["Kernel Name"], []).append(float(row["Metric Value"].replace(",", "")))
-    ours = {k: v for k, v in agg.items() if "ngu::" in k}
+    ours = {k: v for k, v in agg.items()
+            if any(n in k for n in ("scan_topk_kernel", "epilogue_kernel", "append_kernel", "reset_kernel", "log_update_kernel"))}
     per_step = sum(sum(v) / len(v) for v in ours.values())
     out = [f"# {tag}: ncu launch list (gpu__time_duration.sum, --clock-control none)", "", note, "",
            "Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.", "",

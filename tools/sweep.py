@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from ngu_b200.engine import EpisodicEngine
 
-def time_variant(B, N, variant, ctas=0, steps=20, warm=5):
+def time_variant(B, N, variant, ctas=0, steps=200, warm=30):
     eng = EpisodicEngine(B, N, device=0, scan_variant=variant, scan_ctas_per_sm=ctas)
     eng._memory.normal_()
     q = torch.randn(B, 32, device="cuda")
@@ -28,7 +28,7 @@ def time_variant(B, N, variant, ctas=0, steps=20, warm=5):
     return dict(B=B, N=N, variant=variant, ctas=ctas, scan_ms=round(ms, 4), scan_GBs=round(gb / ms * 1e3, 1), step_ms=round(ms2, 4), step_GBs=round(gb / ms2 * 1e3, 1), **g)
 
 if __name__ == "__main__":
-    for (B, N) in [(256, 30000), (64, 5000), (32, 30000), (1024, 30000)]:
+    for (B, N) in [(256, 30000), (1024, 30000)]:
         for v in range(8):
             try:
                 print(json.dumps(time_variant(B, N, v)), flush=True)
