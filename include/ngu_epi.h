@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NGU_EPI_ABI_VERSION 1
+#define NGU_EPI_ABI_VERSION 2
 #define NGU_EPI_DIM 32          /* controllable_state_dim, episodic_novelty.py:23 */
 #define NGU_EPI_MAX_K 32        /* k-NN list lives in one warp */
 
@@ -88,6 +88,7 @@ typedef struct ngu_epi_state {
     int64_t cursor;
     int64_t steps;              /* finished steps since create / set_state */
     int64_t exchange_timeouts;  /* read-only: p2p exchange rounds that timed out waiting for a peer (0 = healthy) */
+    double ll_mean, ll_var, ll_count;   /* LifelongNovelty.ll_rms (lifelong_novelty.py:26), used by ngu_epi_step_rnd */
 } ngu_epi_state;
 
 /* Number of doubles exchanged between shards per step:
@@ -155,6 +156,16 @@ int ngu_epi_reset(ngu_epi* h, const uint8_t* done_dev, void* stream);
  * (episodic_novelty.py:37-84, intrinsic_novelty.py:20-34), all on `stream`. */
 int ngu_epi_step(ngu_epi* h, const float* q_dev, const float* alpha_dev,
                  float* r_int_dev, float* r_epi_dev, void* stream);
+
+/* ngu_epi_step with the scalar tail of LifelongNovelty.compute_lifelong_curiosity fused in
+ * (lifelong_novelty.py:53-57): instead of a ready-made modulator the caller passes the RND
+ * predictor / target features float[n_actors][feat_dim] (feat_dim must be 128,
+ * rnd_prediction.py:27); the library computes err = mean((pred-targ)^2, axis=1), updates ll_rms
+ * (use_mpi=False: local batch mean/std, mpi_util.py:51-52), alpha = 1 + (err - mean)/sqrt(var),
+ * and continues as ngu_epi_step.  alpha_out_dev (float[n_actors], may be NULL) receives alpha.
+ * No device->host sync is needed between the RND forward and the reward. */
+int ngu_epi_step_rnd(ngu_epi* h, const float* q_dev, const float* pred_dev, const float* targ_dev, int32_t feat_dim,
+                     float* r_int_dev, float* r_epi_dev, float* alpha_out_dev, void* stream);
 
 /* Same, with HOST buffers (what the Python drop-in calls with CPU tensors):
  * H2D of q/alpha, the step, D2H of the rewards, synchronous. */

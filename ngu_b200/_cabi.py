@@ -33,6 +33,7 @@ class NguEpiState(C.Structure):
         ("epi_mean", C.c_double), ("epi_var", C.c_double), ("epi_count", C.c_double),
         ("intr_mean", C.c_double), ("intr_var", C.c_double), ("intr_count", C.c_double),
         ("cursor", C.c_int64), ("steps", C.c_int64), ("exchange_timeouts", C.c_int64),
+        ("ll_mean", C.c_double), ("ll_var", C.c_double), ("ll_count", C.c_double),
     ]
 
 
@@ -51,6 +52,7 @@ SYMBOLS = {
     "ngu_epi_append": (C.c_int, [_P, _P, _P]),
     "ngu_epi_reset": (C.c_int, [_P, _P, _P]),
     "ngu_epi_step": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "ngu_epi_step_rnd": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     "ngu_epi_step_host": (C.c_int, [_P, _P, _P, _P, _P]),
     "ngu_epi_reset_host": (C.c_int, [_P, _P]),
     "ngu_epi_topk_host": (C.c_int, [_P, _P, _P]),
@@ -87,7 +89,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the ABI is out of date
         fn.restype = res
         fn.argtypes = args
-    if lib.ngu_epi_abi_version() != 1:
+    if lib.ngu_epi_abi_version() != 2:
         raise NguEpiError("libngu_epi.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -25,7 +25,8 @@ struct DevState {
     double ed_count;
     double epi_mean, epi_var, epi_count;
     double intr_mean, intr_var, intr_count;
-    long long steps;     // the 8 words from ed_count to steps are staged together by the epilogue
+    long long steps;     // the 11 words from ed_count to ll_count are staged together by the epilogue
+    double ll_mean, ll_var, ll_count;   // LifelongNovelty.ll_rms (lifelong_novelty.py:26,54), RND fused path only
     long long cursor;
     long long exchange_timeouts;   // p2p exchange rounds that gave up waiting for a peer (must stay 0)
 };
@@ -42,6 +43,7 @@ struct EpiConsts {
 // therefore a single out-of-line routine, loops are not unrolled, and the pairwise
 // summation is driven by a small host-built plan instead of recursion.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ float sqdiff_rn(float a, float b) { const float d = __fsub_rn(a, b); return __fmul_rn(d, d); }
 __device__ __noinline__ float f32_div(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __noinline__ float f32_rcp(float a) { return __frcp_rn(a); }
 __device__ __noinline__ float f32_sqrt(float a) { return __fsqrt_rn(a); }
@@ -111,7 +113,11 @@ __device__ __forceinline__ float np_pairwise_sum8(const float* v, int stride, co
 // ---------------------------------------------------------------------------
 //   EXCHANGE  (multi-GPU, p2p mode) sum the rank sums - and, after the rewards, the log-only
 //             sums - over all shards through NVLink peer stores (p2p_exchange.cuh)
-enum : int { PH_RANKSUMS = 1, PH_FINISH = 2, PH_APPEND = 4, PH_LOGFUSE = 8, PH_EXCHANGE = 16 };
+//   RND       (with FINISH) the scalar tail of LifelongNovelty.compute_lifelong_curiosity
+//             (lifelong_novelty.py:53-57): err = mean_128((pred-targ)^2), ll_rms update, alpha =
+//             1 + (err - mean)/sqrt(var) - replaces the alpha input; the per-actor error is
+//             computed while the scan is still running
+enum : int { PH_RANKSUMS = 1, PH_FINISH = 2, PH_APPEND = 4, PH_LOGFUSE = 8, PH_EXCHANGE = 16, PH_RND = 32 };
 
 struct EpilogueParams {
     const float* dist;        // [B][k]  sqrt(d2) (reference) or d2 (paper), written by the scan kernel
@@ -129,6 +135,9 @@ struct EpilogueParams {
     int32_t phases;
     int32_t stage_q;          // 1: q fits the dynamic shared memory of this launch
     int32_t pad;
+    const float* rnd_pred;    // [B][128] RND predictor features (PH_RND)
+    const float* rnd_targ;    // [B][128] RND target features
+    float* alpha_out;         // [B] or null: the modulator computed by the RND phase
     P2PView p2p;              // used when phases & PH_EXCHANGE
 };
 
@@ -162,9 +171,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-// Dynamic shared memory of the epilogue: [dist B*k][alpha B][q B*32] floats.
+// Dynamic shared memory of the epilogue: [dist B*k][alpha B][tmp B][q B*32] floats.
 __host__ __device__ inline size_t epilogue_q_offset(int B, int k) {   // floats; keeps q 16-byte aligned
-    return (static_cast<size_t>(B) * (k + 1) + 3) & ~static_cast<size_t>(3);
+    return (static_cast<size_t>(B) * (k + 2) + 3) & ~static_cast<size_t>(3);
 }
 __host__ __device__ inline size_t epilogue_smem_bytes(int B, int k, bool with_q) {
     return (epilogue_q_offset(B, k) + (with_q ? static_cast<size_t>(B) * 32 : 0)) * sizeof(float);
@@ -174,7 +183,8 @@ template <int THREADS>   // THREADS >= 8 * NGU_EPI_MAX_K (8 lanes per column in 
 __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams p, const EpiConsts c) {
     __shared__ double s_sums[2 * 32 + 1];
     __shared__ double s_mean[32], s_var[32];
-    __shared__ double s_scal[8];      // ed_count, epi(mean,var,count), intr(mean,var,count), steps
+    __shared__ double s_scal[12];     // ed_count, epi(mean,var,count), intr(mean,var,count), steps, ll(mean,var,count)
+    __shared__ double s_ll[2];
     __shared__ float mean32[32];
     __shared__ double red[4][THREADS / 32];
     __shared__ long long s_cursor;
@@ -186,6 +196,7 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
     const int B = c.n_actors;
     float* s_dist = s_dyn;                 // [B][k]
     float* s_alpha = s_dist + B * k;       // [B]
+    float* s_tmp = s_alpha + B;            // [B]
     float4* s_q = reinterpret_cast<float4*>(s_dyn + epilogue_q_offset(B, k));   // [B][8]
     DevState* st = p.state;
     const bool finish = (p.phases & PH_FINISH) != 0, append = (p.phases & PH_APPEND) != 0;
@@ -202,20 +213,47 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
     if (append)
         for (int i = threadIdx.x; i < B; i += THREADS) prefetch_l2(p.q + static_cast<int64_t>(i) * 32);
 
+    const bool rnd = finish && (p.phases & PH_RND) != 0;
+    if (rnd) {
+        // err[b] = mean over the 128 features of (pred - targ)^2 in numpy's f32 pairwise order
+        // (n = 128: eight strided accumulators, lifelong_novelty.py:53).  The features were written by
+        // kernels that precede the scan in stream order, so this runs while the scan streams.
+#pragma unroll 1
+        for (int b = threadIdx.x; b < B; b += THREADS) {
+            const float4* P = reinterpret_cast<const float4*>(p.rnd_pred + static_cast<int64_t>(b) * 128);
+            const float4* T = reinterpret_cast<const float4*>(p.rnd_targ + static_cast<int64_t>(b) * 128);
+            float r[8];
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const float4 p0 = __ldg(P + 2 * i), p1 = __ldg(P + 2 * i + 1);
+                const float4 t0 = __ldg(T + 2 * i), t1 = __ldg(T + 2 * i + 1);
+                const float e[8] = {sqdiff_rn(p0.x, t0.x), sqdiff_rn(p0.y, t0.y), sqdiff_rn(p0.z, t0.z), sqdiff_rn(p0.w, t0.w),
+                                    sqdiff_rn(p1.x, t1.x), sqdiff_rn(p1.y, t1.y), sqdiff_rn(p1.z, t1.z), sqdiff_rn(p1.w, t1.w)};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] = (i == 0) ? e[j] : __fadd_rn(r[j], e[j]);
+            }
+            const float sum = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+            s_alpha[b] = __fmul_rn(sum, 1.0f / 128.0f);   // exact: mean = sum / 128
+        }
+    }
+
     asm volatile("griddepcontrol.wait;" ::: "memory");               // scan kernel complete, its writes visible
 
     // ---- one batch of independent loads: everything the phases below need goes on chip ----
 #pragma unroll 1
     for (int i = threadIdx.x; i < B * k; i += THREADS) s_dist[i] = __ldcg(p.dist + i);
     if (finish) {
+        if (!rnd) {
 #pragma unroll 1
-        for (int i = threadIdx.x; i < B; i += THREADS) s_alpha[i] = p.alpha ? __ldcg(p.alpha + i) : 1.0f;
+            for (int i = threadIdx.x; i < B; i += THREADS) s_alpha[i] = p.alpha ? __ldcg(p.alpha + i) : 1.0f;
+        }
         if (p.sums_in && threadIdx.x < 2 * k + 1) s_sums[threadIdx.x] = __ldcg(p.sums_in + threadIdx.x);
         if (threadIdx.x < k) {
             s_mean[threadIdx.x] = __ldcg(&st->ed_mean[threadIdx.x]);
             s_var[threadIdx.x] = __ldcg(&st->ed_var[threadIdx.x]);
         }
-        if (threadIdx.x >= 32 && threadIdx.x < 40) s_scal[threadIdx.x - 32] = __ldcg(&st->ed_count + (threadIdx.x - 32));
+        if (threadIdx.x >= 32 && threadIdx.x < 43) s_scal[threadIdx.x - 32] = __ldcg(&st->ed_count + (threadIdx.x - 32));
     }
     if (append) {
         if (p.stage_q) {
@@ -226,6 +264,50 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
     }
     if (threadIdx.x >= 96 && threadIdx.x < 96 + p.plan_len && threadIdx.x < 160) s_plan[threadIdx.x - 96] = __ldcg(p.plan + (threadIdx.x - 96));
     __syncthreads();
+
+    if (rnd) {
+        // ll_rms.update(err) with use_mpi=False (mpi_util.py:51-52: np.mean / np.std over the local batch,
+        // float32 pairwise sums), then alpha = 1 + (err - mean)/sqrt(var) in float64 (lifelong_novelty.py:54-57)
+        if (threadIdx.x < 32) {
+            const float sm = np_pairwise_sum8(s_alpha, 1, s_plan, p.plan_len, threadIdx.x & 7, s_stack[threadIdx.x]);
+            if (threadIdx.x == 0) s_ll[0] = static_cast<double>(f32_div(sm, static_cast<float>(B)));
+        }
+        __syncthreads();
+        const float bmean = static_cast<float>(s_ll[0]);
+#pragma unroll 1
+        for (int b = threadIdx.x; b < B; b += THREADS) {
+            const float d = __fsub_rn(s_alpha[b], bmean);
+            s_tmp[b] = __fmul_rn(d, d);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const float sv = np_pairwise_sum8(s_tmp, 1, s_plan, p.plan_len, threadIdx.x & 7, s_stack[threadIdx.x]);
+            if (threadIdx.x == 0) {
+                const float nB = static_cast<float>(B);
+                const float b_std = f32_sqrt(f32_div(sv, nB));
+                const float b_var = __fmul_rn(b_std, b_std);                       // np.square(batch_std)
+                const double m_b = static_cast<double>(__fmul_rn(b_var, nB));      // batch_var * batch_count stays f32
+                const double n_b = static_cast<double>(B);
+                const double mean = s_scal[8], var = s_scal[9], count = s_scal[10];
+                const double delta = static_cast<double>(bmean) - mean;
+                const double totc = count + n_b;
+                const double new_mean = mean + f64_div(delta * n_b, totc);
+                const double m2 = var * count + m_b + f64_div(delta * delta * count * n_b, totc);
+                const double new_var = f64_div(m2, totc);
+                st->ll_mean = new_mean; st->ll_var = new_var; st->ll_count = totc;
+                s_ll[0] = new_mean;
+                s_ll[1] = sqrt(new_var);
+            }
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int b = threadIdx.x; b < B; b += THREADS) {
+            const float a = static_cast<float>(1.0 + f64_div(static_cast<double>(s_alpha[b]) - s_ll[0], s_ll[1]));
+            s_alpha[b] = a;
+            if (p.alpha_out) p.alpha_out[b] = a;
+        }
+        __syncthreads();
+    }
 
     if (p.phases & PH_RANKSUMS) {
         if (threadIdx.x < 256) {

@@ -182,6 +182,7 @@ int default_state(ngu_epi* h) {
     s.ed_count = h->cfg.prior_count;                                      // mpi_util.py:42
     s.epi_var = 1.0;  s.epi_count = 1e-4;                                 // RunningMeanStd() defaults
     s.intr_var = 1.0; s.intr_count = 1e-4;
+    s.ll_var = 1.0; s.ll_count = 1e-4;                                    // LifelongNovelty.ll_rms, lifelong_novelty.py:26
     return ngu_epi_set_state(h, &s);
 }
 
@@ -368,9 +369,13 @@ static int launch_scan(ngu_epi* h, const float* q_dev, cudaStream_t s) {
     return NGU_OK;
 }
 
+struct RndArgs { const float* pred; const float* targ; float* alpha_out; };
+
 static int launch_epilogue(ngu_epi* h, int phases, const double* sums_in, const float* alpha, float* r_int,
-                           float* r_epi, double* log_sums, const float* q, cudaStream_t s) {
+                           float* r_epi, double* log_sums, const float* q, cudaStream_t s,
+                           const RndArgs* rnd = nullptr) {
     EpilogueParams ep{};
+    if (rnd) { ep.rnd_pred = rnd->pred; ep.rnd_targ = rnd->targ; ep.alpha_out = rnd->alpha_out; }
     ep.dist = h->dist; ep.rank_sums = h->rank_sums; ep.sums_in = sums_in; ep.alpha = alpha;
     ep.r_int = r_int; ep.r_epi = r_epi; ep.log_sums = log_sums; ep.q = q; ep.memory = h->memory;
     ep.state = h->state; ep.phases = phases & h->debug_phase_mask;
@@ -467,6 +472,20 @@ int ngu_epi_step(ngu_epi* h, const float* q_dev, const float* alpha_dev, float* 
                            r_epi_dev, nullptr, q_dev, s);
 }
 
+int ngu_epi_step_rnd(ngu_epi* h, const float* q_dev, const float* pred_dev, const float* targ_dev, int32_t feat_dim,
+                     float* r_int_dev, float* r_epi_dev, float* alpha_out_dev, void* stream) {
+    if (!h || !q_dev || !pred_dev || !targ_dev || !r_int_dev) return fail(h, NGU_EINVAL, "null argument");
+    if (feat_dim != 128) return fail(h, NGU_EINVAL, "the RND feature width must be 128 (rnd_prediction.py:27)");
+    int rc = bind_device(h);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    rc = launch_scan(h, q_dev, s);
+    if (rc) return rc;
+    RndArgs ra{pred_dev, targ_dev, alpha_out_dev};
+    return launch_epilogue(h, PH_RANKSUMS | PH_FINISH | PH_APPEND | PH_LOGFUSE | PH_RND, nullptr, nullptr, r_int_dev,
+                           r_epi_dev, nullptr, q_dev, s, &ra);
+}
+
 int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host, float* r_int_host,
                       float* r_epi_host) {
     if (!h || !q_host || !r_int_host) return fail(h, NGU_EINVAL, "null argument");
@@ -530,6 +549,7 @@ int ngu_epi_get_state(ngu_epi* h, ngu_epi_state* out) {
     out->epi_mean = d.epi_mean; out->epi_var = d.epi_var; out->epi_count = d.epi_count;
     out->intr_mean = d.intr_mean; out->intr_var = d.intr_var; out->intr_count = d.intr_count;
     out->cursor = d.cursor; out->steps = d.steps; out->exchange_timeouts = d.exchange_timeouts;
+    out->ll_mean = d.ll_mean; out->ll_var = d.ll_var; out->ll_count = d.ll_count;
     return NGU_OK;
 }
 
@@ -546,6 +566,7 @@ int ngu_epi_set_state(ngu_epi* h, const ngu_epi_state* in) {
     d.epi_mean = in->epi_mean; d.epi_var = in->epi_var; d.epi_count = in->epi_count;
     d.intr_mean = in->intr_mean; d.intr_var = in->intr_var; d.intr_count = in->intr_count;
     d.cursor = in->cursor; d.steps = in->steps;
+    d.ll_mean = in->ll_mean; d.ll_var = in->ll_var; d.ll_count = in->ll_count;
     CU_TRY(h, cudaDeviceSynchronize());
     CU_TRY(h, cudaMemcpy(h->state, &d, sizeof d, cudaMemcpyHostToDevice));
     return NGU_OK;

@@ -141,6 +141,21 @@ class EpisodicEngine:
                                      self._stream()), self._h)
         return self._r_int, self._r_epi
 
+    def step_rnd(self, q: torch.Tensor, pred: torch.Tensor, targ: torch.Tensor):
+        """ngu_epi_step_rnd: RND features in, the modulator is computed inside the epilogue kernel.
+        Returns device tensors (r_int, r_epi, alpha)."""
+        self._q_keep = self._q(q)
+        pred = pred.to(device=self.device, dtype=torch.float32).contiguous()
+        targ = targ.to(device=self.device, dtype=torch.float32).contiguous()
+        if tuple(pred.shape) != (self.n_actors, 128) or tuple(targ.shape) != (self.n_actors, 128):
+            raise ValueError("RND features must be (n_actors, 128)")
+        self._rnd_keep = (pred, targ)
+        if not hasattr(self, "_alpha_out"):
+            self._alpha_out = torch.empty(self.n_actors, dtype=torch.float32, device=self.device)
+        check(self._lib.ngu_epi_step_rnd(self._h, _ptr(self._q_keep), _ptr(pred), _ptr(targ), 128, _ptr(self._r_int),
+                                         _ptr(self._r_epi), _ptr(self._alpha_out), self._stream()), self._h)
+        return self._r_int, self._r_epi, self._alpha_out
+
     # ---- host-buffer path (what the drop-in calls with CPU tensors) ---------------
     def step_host(self, q: np.ndarray, alpha: np.ndarray | None = None):
         """ngu_epi_step_host: host float32 arrays in, host float32 rewards (r_int, r_epi) out, synchronous."""
@@ -181,7 +196,8 @@ class EpisodicEngine:
         return dict(ed_mean=np.array(s.ed_mean[:k]), ed_var=np.array(s.ed_var[:k]), ed_count=s.ed_count,
                     epi_mean=s.epi_mean, epi_var=s.epi_var, epi_count=s.epi_count,
                     intr_mean=s.intr_mean, intr_var=s.intr_var, intr_count=s.intr_count,
-                    cursor=int(s.cursor), steps=int(s.steps), exchange_timeouts=int(s.exchange_timeouts))
+                    cursor=int(s.cursor), steps=int(s.steps), exchange_timeouts=int(s.exchange_timeouts),
+                    ll_mean=s.ll_mean, ll_var=s.ll_var, ll_count=s.ll_count)
 
     def set_state(self, st: dict):
         s = NguEpiState()
@@ -189,7 +205,8 @@ class EpisodicEngine:
         for j in range(self.k):
             if "ed_mean" in st: s.ed_mean[j] = float(np.ravel(st["ed_mean"])[j])
             if "ed_var" in st: s.ed_var[j] = float(np.ravel(st["ed_var"])[j])
-        for name in ("ed_count", "epi_mean", "epi_var", "epi_count", "intr_mean", "intr_var", "intr_count"):
+        for name in ("ed_count", "epi_mean", "epi_var", "epi_count", "intr_mean", "intr_var", "intr_count",
+                     "ll_mean", "ll_var", "ll_count"):
             if name in st: setattr(s, name, float(st[name]))
         for name in ("cursor", "steps"):
             if name in st: setattr(s, name, int(st[name]))

@@ -37,7 +37,8 @@ class LifelongNovelty(nn.Module):
     def __init__(self, obs_shape, model_hypr, logger):
         super().__init__()
         self.obs_shape, self.model_hypr, self.logger = obs_shape, model_hypr, logger
-        self.ll_rms = RunningMeanStd(use_mpi=False)
+        self._host_ll_rms = RunningMeanStd(use_mpi=False)
+        self._device_ll_rms = None      # set by IntrinsicNovelty when the fused (on-device) tail is in use
         self.rnd_loss_rms = RunningMeanStd(use_mpi=False)
         self.predictor = RNDPrediction(obs_shape, model_hypr)
         self.target = RNDPrediction(obs_shape, model_hypr)
@@ -50,6 +51,12 @@ class LifelongNovelty(nn.Module):
         self.update_count = 0
         self.grad_hook = None
 
+    @property
+    def ll_rms(self):
+        """Running mean/std of the RND error (lifelong_novelty.py:26).  Lives on the GPU when
+        IntrinsicNovelty runs the fused tail (ngu_epi_step_rnd), on the host otherwise."""
+        return self._device_ll_rms if self._device_ll_rms is not None else self._host_ll_rms
+
     def forward(self, obs):
         return self.predictor(obs), self.target(obs)
 
@@ -58,8 +65,9 @@ class LifelongNovelty(nn.Module):
         """alpha_t (lifelong_novelty.py:49-57); returns a CPU float64 tensor like the reference."""
         pred, targ = self(obs.to(ptu.current_device()))
         err = (pred - targ).pow(2).mean(dim=1).cpu().numpy()
-        self.ll_rms.update(err)
-        return torch.from_numpy(1.0 + (err - self.ll_rms.mean) / np.sqrt(self.ll_rms.var))
+        rms = self._host_ll_rms
+        rms.update(err)
+        return torch.from_numpy(1.0 + (err - rms.mean) / np.sqrt(rms.var))
 
     def step(self, timestep_obs):
         params = list(self.predictor.parameters())

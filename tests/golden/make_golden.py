@@ -150,6 +150,39 @@ def run_case(torch, IntrinsicNovelty, model_hypr, name, B, N, steps, seed, scale
     print(f"{name}: B={B} N={N} steps={steps} reward[0,:3]={out['reward'][0, :3]}")
 
 
+def rnd_features(B, steps):
+    """Synthetic RND (predictor, target) features [steps,B,128] from numpy's platform-independent PCG64."""
+    rng = np.random.default_rng(3100 + B)
+    pred = (rng.standard_normal((steps, B, 128)) * 0.3).astype(np.float32)
+    targ = (rng.standard_normal((steps, B, 128)) * 0.3 + 0.1).astype(np.float32)
+    return pred, targ
+
+
+def run_rnd_case(torch, model_hypr):
+    """Golden for the scalar tail of LifelongNovelty.compute_lifelong_curiosity
+    (lifelong_novelty.py:49-57): the unmodified reference method with its CNN forward replaced by
+    known (predictor, target) features."""
+    from ngu.models.intrinsic_novelty.lifelong_novelty import LifelongNovelty
+    out = {}
+    for B in (1, 6, 64, 256, 300):
+        ll = LifelongNovelty((1, 84, 84), model_hypr, _NullLogger())
+        steps = 12
+        pred, targ = rnd_features(B, steps)
+        alphas, means, vars_, counts = [], [], [], []
+        for t in range(steps):
+            ll.forward = lambda obs, t=t: (torch.from_numpy(pred[t]), torch.from_numpy(targ[t]))
+            a = ll.compute_lifelong_curiosity(torch.zeros(B, 1))      # THE reference call
+            assert a.dtype == torch.float64
+            alphas.append(a.numpy().copy())
+            means.append(float(ll.ll_rms.mean)); vars_.append(float(ll.ll_rms.var)); counts.append(float(ll.ll_rms.count))
+        out[f"alpha_{B}"] = np.stack(alphas)      # inputs are rebuilt from rnd_features(B, steps) by the tests
+        out[f"mean_{B}"], out[f"var_{B}"], out[f"count_{B}"] = np.array(means), np.array(vars_), np.array(counts)
+    out["batches"] = np.array([1, 6, 64, 256, 300])
+    out["versions"] = np.array([f"torch {torch.__version__}", f"numpy {np.__version__}"])
+    np.savez_compressed(os.path.join(HERE, "..", "golden_rnd", "rnd_tail.npz"), **out)
+    print("rnd_tail: alpha[0,:3] =", out["alpha_6"][0, :3])
+
+
 def lane8_probe(torch):
     """torch CPU's D=32 sum order must be the lane-8 order
     on the machine that produced the goldens."""
@@ -171,6 +204,8 @@ def main():
     lane8_probe(torch)
     for case in CASES:
         run_case(torch, IntrinsicNovelty, model_hypr, *case)
+    os.makedirs(os.path.join(HERE, "..", "golden_rnd"), exist_ok=True)
+    run_rnd_case(torch, model_hypr)
 
 
 if __name__ == "__main__":

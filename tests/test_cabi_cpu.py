@@ -25,13 +25,13 @@ def test_exports_every_header_symbol(lib):
     assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.ngu_epi_abi_version() == 1
+    assert lib.ngu_epi_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
     from ngu_b200 import _cabi
     assert C.sizeof(_cabi.NguEpiCfg) == 64
-    assert C.sizeof(_cabi.NguEpiState) == 8 * (32 + 32 + 1 + 6) + 24
+    assert C.sizeof(_cabi.NguEpiState) == 8 * (32 + 32 + 1 + 6) + 24 + 24
 
 
 def test_create_rejects_bad_config_and_missing_gpu(lib):

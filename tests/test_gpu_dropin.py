@@ -83,3 +83,70 @@ def test_full_dropin_with_real_cnn_producers(cuda_device):
     sd = inn.epi_novel.state_dict()
     inn.epi_novel.load_state_dict(sd)
     assert inn.epi_novel.memory_idx == sd["engine"]["cursor"]
+
+
+@pytest.mark.parametrize("B", [1, 6, 64, 256, 300])
+def test_fused_rnd_tail_matches_reference_golden(cuda_device, B):
+    """ngu_epi_step_rnd: err / ll_rms / alpha computed inside the epilogue kernel vs the reference's
+    compute_lifelong_curiosity output (tests/golden_rnd/rnd_tail.npz) and the episodic oracle."""
+    import os
+    from ngu_b200.engine import EpisodicEngine
+    from oracle.episodic_oracle import EpisodicOracle
+    from tests.conftest import ROOT
+    from tests.golden.make_golden import rnd_features
+    g = np.load(os.path.join(ROOT, "tests", "golden_rnd", "rnd_tail.npz"))
+    pred, targ = rnd_features(B, 12)
+    N = 400
+    rng = np.random.default_rng(B)
+    mem0 = rng.standard_normal((N, B, 32), dtype=np.float32)
+    eng = EpisodicEngine(B, N, device=0)
+    eng.load_memory(mem0)
+    orc = EpisodicOracle(B, N)
+    orc.memory[...] = mem0
+    for t in range(12):
+        q = rng.standard_normal((B, 32), dtype=np.float32)
+        r_int, r_epi, alpha = eng.step_rnd(torch.from_numpy(q).cuda(), torch.from_numpy(pred[t]).cuda(),
+                                           torch.from_numpy(targ[t]).cuda())
+        want_alpha = g[f"alpha_{B}"][t]
+        np.testing.assert_allclose(alpha.cpu().numpy(), want_alpha, rtol=2e-6, atol=2e-6)
+        st = eng.get_state()
+        assert abs(st["ll_mean"] - g[f"mean_{B}"][t]) <= 1e-12 * abs(g[f"mean_{B}"][t]) + 1e-15
+        assert abs(st["ll_var"] - g[f"var_{B}"][t]) <= 1e-12 * abs(g[f"var_{B}"][t]) + 1e-18
+        assert st["ll_count"] == g[f"count_{B}"][t]
+        want = orc.step(q, want_alpha)
+        rel = np.abs(r_int.cpu().numpy() - want["reward"]) / np.abs(want["reward"])
+        assert rel.max() <= 1e-5
+    eng.close()
+
+
+def test_cuda_graph_replay_equals_eager(cuda_device):
+    """The graph-replayed step (H2D + CNNs + scan + epilogue + D2H) gives the same rewards, memory and
+    trackers as the eager drop-in, step after step, including resets between replays."""
+    import copy
+    import ngu_b200.pytorch_util as ptu
+    from ngu_b200.engine import DEFAULT_HYPR
+    from ngu_b200.intrinsic_novelty import IntrinsicNovelty
+    ptu.init_device()
+    B, N = 16, 500
+    hy = dict(DEFAULT_HYPR, episodic_memory_capacity=N)
+    torch.manual_seed(0)
+    a = IntrinsicNovelty(B, 18, (1, 84, 84), hy, _NullLogger()).to(ptu.device)
+    b = IntrinsicNovelty(B, 18, (1, 84, 84), hy, _NullLogger()).to(ptu.device)
+    b.epi_novel.embedding.load_state_dict(copy.deepcopy(a.epi_novel.embedding.state_dict()))
+    b.ll_novel.load_state_dict(copy.deepcopy(a.ll_novel.state_dict()))
+    b.enable_cuda_graph()
+    g = torch.Generator().manual_seed(1)
+    for t in range(8):
+        obs = torch.randn(B, 1, 84, 84, generator=g).clamp_(-5, 5)
+        ra = a.compute_intrinsic_novelty(obs)
+        rb = b.compute_intrinsic_novelty(obs)
+        assert torch.allclose(ra, rb, rtol=1e-5, atol=0), (t, (ra - rb).abs().max())
+        done = torch.zeros(B, dtype=torch.bool)
+        done[(3 * t) % B] = True
+        a.reset_memory_if_done(done)
+        b.reset_memory_if_done(done)
+    assert b._graphed.replays == 8
+    assert torch.allclose(a.epi_novel.episodic_memory, b.epi_novel.episodic_memory, rtol=1e-5, atol=1e-6)
+    assert a.epi_novel.memory_idx == b.epi_novel.memory_idx == 8
+    np.testing.assert_allclose(a.epi_novel.ed_rms.mean, b.epi_novel.ed_rms.mean, rtol=1e-5)
+    np.testing.assert_allclose(a.ll_novel.ll_rms.mean, b.ll_novel.ll_rms.mean, rtol=1e-5)

@@ -106,3 +106,21 @@ def test_multi_rank_mean_matches_single_rank_within_tolerance():
         r1 = a.step(q, None, n_ranks=1)["reward"]
         r4 = b.step(q, None, n_ranks=4)["reward"]
         assert _rel(r4, r1).max() < 1e-6
+
+
+@pytest.mark.parametrize("B", [1, 6, 64, 256, 300])
+def test_rnd_tail_oracle_matches_reference_golden(B):
+    """lifelong_novelty.py:53-57 restated (oracle.LifelongTailOracle) vs the reference's own output."""
+    import os
+    from oracle.episodic_oracle import LifelongTailOracle
+    from tests.conftest import ROOT
+    from tests.golden.make_golden import rnd_features
+    g = np.load(os.path.join(ROOT, "tests", "golden_rnd", "rnd_tail.npz"))
+    pred, targ = rnd_features(B, 12)
+    o = LifelongTailOracle()
+    for t in range(12):
+        a = o.modulator(pred[t], targ[t])
+        np.testing.assert_allclose(a, g[f"alpha_{B}"][t], rtol=1e-12, atol=1e-12)
+        assert abs(o.mean - g[f"mean_{B}"][t]) <= 1e-15 + 1e-12 * abs(g[f"mean_{B}"][t])
+        assert abs(o.var - g[f"var_{B}"][t]) <= 1e-12 * abs(g[f"var_{B}"][t]) + 1e-18
+        assert float(o.count) == g[f"count_{B}"][t]
