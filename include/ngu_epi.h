@@ -193,11 +193,15 @@ int ngu_epi_dump_memory_host(ngu_epi* h, float* slot_major_host);
  *   1. every rank:  ngu_epi_p2p_export(h, handle [64 bytes out], world)
  *   2. all-gather the 64-byte handles in rank order (any transport)
  *   3. every rank:  ngu_epi_p2p_connect(h, rank, world, handles [world*64 bytes])
- * Afterwards ngu_epi_step / ngu_epi_step_host sum the rank sums (and the log-only sums) over all
- * ranks inside the epilogue kernel; all ranks must call them in lockstep.  Ranks must sit on
- * DISTINCT GPUs (the kernel spins on flags written by the peers). */
+ * Afterwards ngu_epi_step / ngu_epi_step_rnd / ngu_epi_step_host sum the rank sums over all ranks
+ * inside the epilogue kernel (one exchange per step); all ranks must call them in lockstep.  Ranks
+ * must sit on DISTINCT GPUs (the kernel polls words written by the peers).  The log-only sums
+ * (epi_novel_rms, intrinsic_novel_rms; never read by the hot path) ride on the NEXT step's
+ * exchange, so those two trackers lag one step; ngu_epi_log_flush (collective: every rank, same
+ * point of its stream) brings them up to date before they are read.  A no-op unless connected. */
 int ngu_epi_p2p_export(ngu_epi* h, void* ipc_handle_out, int32_t world);
 int ngu_epi_p2p_connect(ngu_epi* h, int32_t rank, int32_t world, const void* ipc_handles);
+int ngu_epi_log_flush(ngu_epi* h, void* stream);
 
 /* Introspection for bench.py / DESIGN.md: kernels launched by the handle so far,
  * and the scan launch geometry {grid, block, dyn_smem, tiles_per_warp, stages, tile_rows}. */

@@ -25,8 +25,10 @@ struct DevState {
     double ed_count;
     double epi_mean, epi_var, epi_count;
     double intr_mean, intr_var, intr_count;
-    long long steps;     // the 11 words from ed_count to ll_count are staged together by the epilogue
+    long long steps;     // the 16 words from ed_count to pending_log are staged together by the epilogue
     double ll_mean, ll_var, ll_count;   // LifelongNovelty.ll_rms (lifelong_novelty.py:26,54), RND fused path only
+    double pending_log[5];              // p2p mode: this shard's log-only sums of the last step, not yet exchanged
+    long long flush_seq;                // sequence number of on-demand log flush rounds
     long long cursor;
     long long exchange_timeouts;   // p2p exchange rounds that gave up waiting for a peer (must stay 0)
 };
@@ -164,6 +166,19 @@ __device__ __noinline__ void log_rms_apply(double* sc, const double* ls) {
 }
 __device__ __forceinline__ long long st_steps_plus_one(double raw) { return __double_as_longlong(raw) + 1; }
 
+// Tracker `which` (0: epi_novel_rms, 1: intrinsic_novel_rms) absorbs the batch described by
+// ls = {sum r_epi, sum r_epi^2, sum r_int, sum r_int^2, count}; sc = the staged scalar block.
+__device__ __forceinline__ void apply_log_sums(DevState* st, double* s_scal, const double* ls, int which) {
+    const double n = ls[4];
+    if (n > 0.0) {
+        const int o = 2 * which;
+        const double m = f64_div(ls[o], n), v = fmax(f64_div(ls[o + 1], n) - m * m, 0.0);
+        double* sc = s_scal + 1 + 3 * which;
+        rms_merge(&sc[0], &sc[1], &sc[2], m, v, n);
+        for (int q = 0; q < 3; ++q) (&st->ed_count)[1 + 3 * which + q] = sc[q];
+    }
+}
+
 // torch.max(x, 0) semantics (NaN propagates), episodic_novelty.py:60-65
 __device__ __forceinline__ float relu_nanprop(float x) { return (x != x) ? x : (x > 0.0f ? x : 0.0f); }
 
@@ -181,9 +196,10 @@ __host__ __device__ inline size_t epilogue_smem_bytes(int B, int k, bool with_q)
 
 template <int THREADS>   // THREADS >= 8 * NGU_EPI_MAX_K (8 lanes per column in the rank-sum pass)
 __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams p, const EpiConsts c) {
-    __shared__ double s_sums[2 * 32 + 1];
+    __shared__ double s_sums[2 * 32 + 1 + 5 + 2];   // rank sums (+ piggybacked log sums in p2p mode)
     __shared__ double s_mean[32], s_var[32];
-    __shared__ double s_scal[12];     // ed_count, epi(mean,var,count), intr(mean,var,count), steps, ll(mean,var,count)
+    __shared__ double s_scal[16];     // ed_count, epi(mean,var,count), intr(mean,var,count), steps, ll(mean,var,count), pending_log[5]
+    __shared__ double s_recv[kMaxWorld * 72];   // p2p receive scratch
     __shared__ double s_ll[2];
     __shared__ float mean32[32];
     __shared__ double red[4][THREADS / 32];
@@ -253,7 +269,7 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
             s_mean[threadIdx.x] = __ldcg(&st->ed_mean[threadIdx.x]);
             s_var[threadIdx.x] = __ldcg(&st->ed_var[threadIdx.x]);
         }
-        if (threadIdx.x >= 32 && threadIdx.x < 43) s_scal[threadIdx.x - 32] = __ldcg(&st->ed_count + (threadIdx.x - 32));
+        if (threadIdx.x >= 32 && threadIdx.x < 48) s_scal[threadIdx.x - 32] = __ldcg(&st->ed_count + (threadIdx.x - 32));
     }
     if (append) {
         if (p.stage_q) {
@@ -338,10 +354,18 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
     }
 
     const bool exchange = (p.phases & PH_EXCHANGE) != 0;
-    const unsigned long long step_id = exchange ? static_cast<unsigned long long>(__double_as_longlong(s_scal[7])) : 0ull;
-    if (exchange) {   // round 1: global rank sums (mpi_util.py:17)
-        if (!p2p_allreduce<THREADS>(p.p2p, s_sums, 2 * k + 1, 0, kSlotFlag1, step_id) && threadIdx.x == 0)
+    if (exchange) {
+        // ONE exchange per step: this step's rank sums (mpi_util.py:17) and, piggybacked, the log-only
+        // sums of the PREVIOUS step (episodic_novelty.py:82, intrinsic_novelty.py:32) - the trackers they
+        // feed are never read by the hot path, so they are brought up to date one step late (or on
+        // demand: ngu_epi_log_flush) instead of paying a second rendezvous per step.
+        const unsigned long long step_id = static_cast<unsigned long long>(__double_as_longlong(s_scal[7]));
+        if (threadIdx.x < 5) s_sums[2 * k + 1 + threadIdx.x] = s_scal[11 + threadIdx.x];
+        __syncthreads();
+        if (!p2p_allreduce<THREADS>(p.p2p, s_sums, 2 * k + 6, 0, step_id, s_recv) && threadIdx.x == 0)
             atomicAdd(reinterpret_cast<unsigned long long*>(&st->exchange_timeouts), 1ull);
+        if (threadIdx.x < 2) apply_log_sums(st, s_scal, s_sums + 2 * k + 1, threadIdx.x);
+        __syncthreads();
     }
 
     if (finish) {
@@ -422,18 +446,10 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
             __syncthreads();
             if (p.log_sums && threadIdx.x < 5) p.log_sums[threadIdx.x] = s_log[threadIdx.x];
             if (p.phases & PH_LOGFUSE) {
-                if (exchange) {   // round 2: global log-only sums (episodic_novelty.py:82, intrinsic_novelty.py:32)
-                    if (!p2p_allreduce<THREADS>(p.p2p, s_log, 5, kSlotLog, kSlotFlag2, step_id) && threadIdx.x == 0)
-                        atomicAdd(reinterpret_cast<unsigned long long*>(&st->exchange_timeouts), 1ull);
-                }
-                if (threadIdx.x < 2) {
-                    // lane 0: epi_novel_rms, lane 1: intrinsic_novel_rms (staged in s_scal[1..6])
-                    const int o = 2 * threadIdx.x;
-                    const double n = s_log[4];
-                    const double m = f64_div(s_log[o], n), v = fmax(f64_div(s_log[o + 1], n) - m * m, 0.0);
-                    double* sc = s_scal + 1 + 3 * threadIdx.x;
-                    rms_merge(&sc[0], &sc[1], &sc[2], m, v, n);
-                    for (int q = 0; q < 3; ++q) (&st->ed_count)[1 + 3 * threadIdx.x + q] = sc[q];
+                if (exchange) {          // p2p mode: keep them for the next step's exchange
+                    if (threadIdx.x < 5) st->pending_log[threadIdx.x] = s_log[threadIdx.x];
+                } else if (threadIdx.x < 2) {
+                    apply_log_sums(st, s_scal, s_log, threadIdx.x);
                 }
             }
         }
@@ -450,6 +466,24 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
         }
         if (threadIdx.x == 64) st->cursor = (cur + 1) % c.capacity;
     }
+}
+
+// On-demand flush of the deferred log-only sums (p2p mode): one exchange round of 5 doubles,
+// then the tracker update; all ranks must launch it together.
+__global__ void __launch_bounds__(128) log_flush_kernel(DevState* st, P2PView v) {
+    __shared__ double s_scal[16];
+    __shared__ double s_vals[8];
+    __shared__ double s_recv[kMaxWorld * 8];
+    if (threadIdx.x < 16) s_scal[threadIdx.x] = __ldcg(&st->ed_count + threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x < 5) s_vals[threadIdx.x] = s_scal[11 + threadIdx.x];
+    __syncthreads();
+    const unsigned long long seq = static_cast<unsigned long long>(st->flush_seq);
+    if (!p2p_allreduce<128>(v, s_vals, 5, kFlushElem, seq, s_recv) && threadIdx.x == 0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&st->exchange_timeouts), 1ull);
+    if (threadIdx.x < 2) apply_log_sums(st, s_scal, s_vals, threadIdx.x);
+    if (threadIdx.x < 5) st->pending_log[threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) st->flush_seq = static_cast<long long>(seq + 1);
 }
 
 __global__ void log_update_kernel(DevState* st, const double* log_sums) {

@@ -98,7 +98,7 @@ struct ngu_epi {
     int2* plan_dev = nullptr;        // pairwise-sum plan for n = B (epilogue rank sums)
     int plan_len = 0;
     // p2p rank-sum exchange (multi-GPU): local inbox + IPC-mapped peer inboxes
-    double* inbox = nullptr;
+    unsigned long long* inbox = nullptr;
     P2PView p2p{};
     bool p2p_connected = false;
     DevState* state = nullptr;
@@ -613,7 +613,7 @@ int ngu_epi_p2p_export(ngu_epi* h, void* ipc_handle_out, int32_t world) {
     int rc = bind_device(h);
     if (rc) return rc;
     if (!h->inbox) {
-        const size_t bytes = static_cast<size_t>(2) * world * kSlotDoubles * sizeof(double);
+        const size_t bytes = static_cast<size_t>(2) * world * kSlotWords * sizeof(unsigned long long);
         CU_TRY(h, cudaMalloc(&h->inbox, bytes));
         CU_TRY(h, cudaMemset(h->inbox, 0, bytes));
         CU_TRY(h, cudaDeviceSynchronize());
@@ -639,9 +639,20 @@ int ngu_epi_p2p_connect(ngu_epi* h, int32_t rank, int32_t world, const void* ipc
         std::memcpy(&hd, static_cast<const char*>(ipc_handles) + 64 * g, sizeof hd);
         void* ptr = nullptr;
         CU_TRY(h, cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
-        h->p2p.peer[g] = static_cast<double*>(ptr);
+        h->p2p.peer[g] = static_cast<unsigned long long*>(ptr);
     }
     h->p2p_connected = true;
+    return NGU_OK;
+}
+
+int ngu_epi_log_flush(ngu_epi* h, void* stream) {
+    if (!h) return fail(h, NGU_EINVAL, "null argument");
+    if (!h->p2p_connected) return NGU_OK;     // nothing is deferred outside p2p mode
+    int rc = bind_device(h);
+    if (rc) return rc;
+    log_flush_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->state, h->p2p);
+    CU_TRY(h, cudaGetLastError());
+    h->launches += 1;
     return NGU_OK;
 }
 

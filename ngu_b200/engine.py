@@ -235,6 +235,10 @@ class EpisodicEngine:
         assert len(blob) == 64 * world
         check(self._lib.ngu_epi_p2p_connect(self._h, int(rank), int(world), blob), self._h)
 
+    def log_flush(self):
+        """Collective (p2p mode): bring the one-step-late log-only trackers up to date."""
+        check(self._lib.ngu_epi_log_flush(self._h, self._stream()), self._h)
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.ngu_epi_launch_count(self._h))

@@ -88,3 +88,9 @@ class ShardedEpisodicEngine:
 
     def reset(self, done_local: torch.Tensor):
         self.engine.reset(done_local)
+
+    def get_state(self) -> dict:
+        """Collective in p2p mode (flushes the deferred log-only sums first)."""
+        if self.exchange == "p2p":
+            self.engine.log_flush()
+        return self.engine.get_state()

@@ -58,8 +58,12 @@ def main():
         assert rel.max() <= 1e-5, f"rank {rank} step {t}: reward rel err {rel.max():.2e}"
         orc.reset(done)
         sh.reset(torch.from_numpy(done[sh.lo:sh.hi]))
-    st = sh.engine.get_state()
+    st = sh.get_state()          # collective in p2p mode: flushes the one-step-late log-only sums
     np.testing.assert_allclose(st["ed_mean"], orc.ed_rms.mean, rtol=1e-6)
+    if sh.exchange != "collective" or sh.track_log_stats:
+        # log-only trackers saw every actor of every step (global count), on every rank
+        assert abs(st["epi_count"] - (1e-4 + args.steps * B)) < 1e-6, st["epi_count"]
+        assert abs(st["intr_count"] - (1e-4 + args.steps * B)) < 1e-6
     assert st["ed_count"] == float(orc.ed_rms.count)            # global actor count went into the tracker
     assert np.array_equal(sh.engine.dump_memory(), orc.memory[:, sh.lo:sh.hi])
     # every rank holds the same replicated statistics
