@@ -212,6 +212,10 @@ int ngu_epi_scan_geometry(const ngu_epi* h, int32_t out[6]);
  * the scan kernel (kernel A alone, not the merge) with CUDA events on the launching
  * stream; _end synchronises and returns the summed device time and the number of
  * launches timed. */
+/* Debug aid (tools/scan_timeline.py; handle created with NGU_EPI_DEBUG_TIMELINE=1 in the environment):
+ * per-warp {kernel start, first tile landed, scan done, flush/merge done} %globaltimer stamps (ns) of
+ * the last scan launch; returns the number of warps copied (<= max_warps) or a negative error. */
+int ngu_epi_debug_timeline(ngu_epi* h, uint64_t* out_host, int32_t max_warps);
 int ngu_epi_scan_timing_begin(ngu_epi* h, int32_t max_calls);
 int ngu_epi_scan_timing_end(ngu_epi* h, double* total_ms, int32_t* calls);
 

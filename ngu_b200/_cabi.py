@@ -65,6 +65,7 @@ SYMBOLS = {
     "ngu_epi_log_flush": (C.c_int, [_P, _P]),
     "ngu_epi_launch_count": (C.c_int64, [_P]),
     "ngu_epi_scan_geometry": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "ngu_epi_debug_timeline": (C.c_int, [_P, _P, C.c_int32]),
     "ngu_epi_scan_timing_begin": (C.c_int, [_P, C.c_int32]),
     "ngu_epi_scan_timing_end": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
 }

@@ -103,6 +103,7 @@ struct ngu_epi {
     bool p2p_connected = false;
     DevState* state = nullptr;
     bool use_pdl = true;
+    unsigned long long* timeline = nullptr;   // NGU_EPI_DEBUG_TIMELINE=1: per-warp timestamps of the last scan
     int debug_phase_mask = ~0;       // NGU_EPI_DEBUG_PHASES: experiments only (tools/sweep.py)
     // staging for the *_host entry points
     cudaStream_t own_stream = nullptr;
@@ -252,6 +253,13 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
     CREATE_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(&epilogue_kernel<kEpilogueThreads>),
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kEpilogueStageBytes)));
     if (const char* e = getenv("NGU_EPI_PDL")) h->use_pdl = atoi(e) != 0;
+    if (const char* e = getenv("NGU_EPI_DEBUG_TIMELINE")) {
+        if (atoi(e) != 0) {
+            const size_t n = static_cast<size_t>(prop.multiProcessorCount) * 4 * 32 * 4;   // >= max warps * 4
+            CREATE_TRY(cudaMalloc(&h->timeline, n * sizeof(unsigned long long)));
+            CREATE_TRY(cudaMemset(h->timeline, 0, n * sizeof(unsigned long long)));
+        }
+    }
     if (const char* e = getenv("NGU_EPI_DEBUG_PHASES")) h->debug_phase_mask = atoi(e);
     plan_geometry(h);
 
@@ -320,7 +328,7 @@ void ngu_epi_destroy(ngu_epi* h) {
     cudaFree(h->inbox);
     if (h->owns_memory) cudaFree(h->memory);
     cudaFree(h->partial); cudaFree(h->topk_d2); cudaFree(h->topk_idx); cudaFree(h->dist);
-    cudaFree(h->rank_sums); cudaFree(h->log_sums); cudaFree(h->state); cudaFree(h->actor_arrivals); cudaFree(h->plan_dev);
+    cudaFree(h->rank_sums); cudaFree(h->log_sums); cudaFree(h->state); cudaFree(h->actor_arrivals); cudaFree(h->plan_dev); cudaFree(h->timeline);
     cudaFree(h->q_stage_dev); cudaFree(h->done_stage_dev);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->r_mapped) cudaFreeHost(h->r_mapped);
@@ -360,6 +368,7 @@ static int launch_scan(ngu_epi* h, const float* q_dev, cudaStream_t s) {
     sp.max_parts = h->max_parts; sp.total_tiles = h->total_tiles;
     sp.actor_arrivals = h->actor_arrivals;
     sp.topk_d2 = h->topk_d2; sp.topk_idx = h->topk_idx; sp.dist = h->dist;
+    sp.timeline = h->timeline;
     void* args[] = {&h->tmap, &sp};
     const bool timed = h->t_used < h->t_beg.size();
     if (timed) CU_TRY(h, cudaEventRecord(h->t_beg[h->t_used], s));
@@ -654,6 +663,18 @@ int ngu_epi_log_flush(ngu_epi* h, void* stream) {
     CU_TRY(h, cudaGetLastError());
     h->launches += 1;
     return NGU_OK;
+}
+
+int ngu_epi_debug_timeline(ngu_epi* h, uint64_t* out_host, int32_t max_warps) {
+    if (!h || !out_host) return fail(h, NGU_EINVAL, "null argument");
+    if (!h->timeline) return fail(h, NGU_ESTATE, "create the handle with NGU_EPI_DEBUG_TIMELINE=1");
+    int rc = bind_device(h);
+    if (rc) return rc;
+    const int warps = h->grid * h->var.warps;
+    const int n = warps < max_warps ? warps : max_warps;
+    CU_TRY(h, cudaDeviceSynchronize());
+    CU_TRY(h, cudaMemcpy(out_host, h->timeline, static_cast<size_t>(n) * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return n;
 }
 
 int64_t ngu_epi_launch_count(const ngu_epi* h) { return h ? h->launches : 0; }

@@ -59,7 +59,24 @@ struct ScanParams {
     float* topk_d2;          // [B][k]
     int32_t* topk_idx;       // [B][k]
     float* dist;             // [B][k]
+    unsigned long long* timeline;  // debug (tools/scan_timeline.py): per warp {start, first tile, scan end, flush end} ns, or null
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Release-only arrival.  Deliberately not __threadfence() + atomicAdd: __threadfence() compiles to
+// MEMBAR.SC.GPU + CCTL.IVALL (a sequentially consistent fence plus an L1 invalidate); the release
+// form is MEMBAR.ALL.GPU + ATOMG and is all the writer side needs.
+__device__ __forceinline__ unsigned atom_add_release_gpu(unsigned* addr, unsigned v) {
+    unsigned old;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;"
+                 : "=r"(old) : "l"(__cvta_generic_to_global(addr)), "r"(v) : "memory");
+    return old;
+}
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -89,22 +106,35 @@ __device__ __forceinline__ void flush_actor(const ScanParams& p, int actor, int6
     const int k = p.k;
     u64* base = p.partial + static_cast<int64_t>(actor) * p.max_parts * k;
     if (lane < k) base[(gw - first) * k + lane] = top.lkey;
-    __threadfence();
-    __syncwarp();
+    __syncwarp();    // orders every lane's list store before lane 0's release below
     unsigned prev = 0;
-    if (lane == 0) prev = atomicAdd(p.actor_arrivals + actor, 1u);
+    if (lane == 0) prev = atom_add_release_gpu(p.actor_arrivals + actor, 1u);
     prev = __shfl_sync(kFull, prev, 0);
     if (prev != static_cast<unsigned>(nparts - 1)) return;
-    // last arrival: every partial list of this actor is in L2
+    // last arrival: every partial list of this actor is in L2 (acquire side: one full fence, B times per launch)
     __threadfence();
     if (lane == 0) p.actor_arrivals[actor] = 0;   // re-arm for the next launch
+    // Pass 1: every partial list that is full proves "k keys >= its k-th entry exist", so the largest
+    // of those k-th entries T is a lower bound of the final k-th best key.  Seeding the merge with it
+    // (floor = T-1: keys are integers and T itself must stay eligible) leaves only a few dozen real
+    // candidates however many lists there are, instead of sorting all nparts*k keys.
+    u64 T = 0ull;
+    for (int l = lane; l < nparts; l += 32) T = umax64(T, __ldcg(base + l * k + (k - 1)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) T = umax64(T, __shfl_xor_sync(kFull, T, o));
     WarpTopK m;
-    m.reset();
+    m.reset(T ? T - 1ull : 0ull);
+    // Pass 2: offer all keys, four independent loads in flight per lane.
     const int nkeys = nparts * k;
-    for (int i0 = 0; i0 < nkeys; i0 += 32) {
-        const int i = i0 + lane;
-        const u64 key = i < nkeys ? __ldcg(base + i) : 0ull;
-        m.offer(key, lane, k);
+    for (int i0 = 0; i0 < nkeys; i0 += 128) {
+        u64 key[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u + lane;
+            key[u] = i < nkeys ? __ldcg(base + i) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) m.offer(key[u], lane, k);
     }
     write_knn(p, actor, m, lane);
 }
@@ -217,6 +247,8 @@ __global__ void __launch_bounds__(WARPS * 32) scan_topk_kernel(const __grid_cons
 
     pdl_launch_dependents();   // the epilogue kernel may become resident now; it waits on us
     const int64_t gw = static_cast<int64_t>(blockIdx.x) * WARPS + warp;
+    const unsigned long long tl0 = p.timeline ? globaltimer_ns() : 0ull;
+    unsigned long long tl1 = 0ull;
     const int64_t t_begin = gw * p.tiles_per_warp;
     int64_t t_end = t_begin + p.tiles_per_warp;
     if (t_end > p.total_tiles) t_end = p.total_tiles;
@@ -275,6 +307,7 @@ __global__ void __launch_bounds__(WARPS * 32) scan_topk_kernel(const __grid_cons
         }
 
         mbar_wait(my_bars + 8 * stage, parity);
+        if (p.timeline && t == t_begin) tl1 = globaltimer_ns();
         const uint32_t tile = my_tiles + stage * Cfg::kTileBytes;
         const int row0 = ti * Cfg::kTileRows;
         float d2[RPL];
@@ -302,7 +335,12 @@ __global__ void __launch_bounds__(WARPS * 32) scan_topk_kernel(const __grid_cons
         if (++ti == tpa) { ti = 0; ++b; }
     }
 
+    const unsigned long long tl2 = p.timeline ? globaltimer_ns() : 0ull;
     flush_actor(p, cur, gw, top, lane);
+    if (p.timeline && lane == 0) {
+        unsigned long long* o = p.timeline + gw * 4;
+        o[0] = tl0; o[1] = tl1; o[2] = tl2; o[3] = globaltimer_ns();
+    }
 }
 
 }  // namespace ngu

@@ -40,9 +40,10 @@ __device__ __forceinline__ int32_t key_slot(u64 key) {
 
 struct WarpTopK {
     u64 lkey;   // lane j: j-th best key (descending over lanes)
-    u64 thr;    // key at lane k-1 (warp-uniform): a candidate must beat it
+    u64 thr;    // max(floor, key at lane k-1) (warp-uniform): a candidate must beat it
+    u64 floor;  // externally known strict lower bound of every key worth keeping (0 = none)
 
-    __device__ __forceinline__ void reset() { lkey = 0; thr = 0; }
+    __device__ __forceinline__ void reset(u64 lower_bound = 0ull) { lkey = 0; thr = lower_bound; floor = lower_bound; }
 
     // Offer one key per lane.  `k` is warp-uniform, 1..32.  The common case (nobody
     // beats the k-th best) is 2 compares + 1 vote.  (The slow path stays inline: an
@@ -67,7 +68,7 @@ struct WarpTopK {
                 const u64 up = __shfl_up_sync(kFull, lkey, 1);
                 if (lane == pos) lkey = c;
                 else if (lane > pos) lkey = up;
-                thr = __shfl_sync(kFull, lkey, k - 1);
+                thr = umax64(floor, __shfl_sync(kFull, lkey, k - 1));
             }
         }
     }
@@ -94,7 +95,7 @@ struct WarpTopK {
             z = ((lane & j) == 0) ? umax64(z, o) : umin64(z, o);
         }
         lkey = z;
-        thr = __shfl_sync(kFull, lkey, k - 1);
+        thr = umax64(floor, __shfl_sync(kFull, lkey, k - 1));
     }
 };
 
