@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NGU_EPI_ABI_VERSION 2
+#define NGU_EPI_ABI_VERSION 3
 #define NGU_EPI_DIM 32          /* controllable_state_dim, episodic_novelty.py:23 */
 #define NGU_EPI_MAX_K 32        /* k-NN list lives in one warp */
 
@@ -204,17 +204,23 @@ int ngu_epi_p2p_connect(ngu_epi* h, int32_t rank, int32_t world, const void* ipc
 int ngu_epi_log_flush(ngu_epi* h, void* stream);
 
 /* Introspection for bench.py / DESIGN.md: kernels launched by the handle so far,
- * and the scan launch geometry {grid, block, dyn_smem, tiles_per_warp, stages, tile_rows}. */
+ * and the scan launch geometry {grid, block, dyn_smem, static tiles per warp, stages, tile_rows,
+ * dynamic chunk tiles (0 = static schedule), chunks in the schedule}. */
 int64_t ngu_epi_launch_count(const ngu_epi* h);
-int ngu_epi_scan_geometry(const ngu_epi* h, int32_t out[6]);
+int ngu_epi_scan_geometry(const ngu_epi* h, int32_t out[8]);
+/* Test aid: tile range [out[0], out[1]) of chunk `idx` (0 <= idx < chunks) of the scan kernel's work
+ * schedule, in units of tiles of tile_rows memory slots over the linear space actor * tiles_per_actor +
+ * tile; the ranges of all chunks partition that space (tests/test_gpu_parity.py). */
+int ngu_epi_debug_chunk(const ngu_epi* h, int32_t idx, int32_t out[2]);
 
 /* Measurement aid (bench.py "roofline"): bracket the next `max_calls` launches of
  * the scan kernel (kernel A alone, not the merge) with CUDA events on the launching
  * stream; _end synchronises and returns the summed device time and the number of
  * launches timed. */
 /* Debug aid (tools/scan_timeline.py; handle created with NGU_EPI_DEBUG_TIMELINE=1 in the environment):
- * per-warp {kernel start, first tile landed, scan done, flush/merge done} %globaltimer stamps (ns) of
- * the last scan launch; returns the number of warps copied (<= max_warps) or a negative error. */
+ * per-warp records of 8 words {kernel start, first tile landed, scan done, flush/merge done (%globaltimer, ns),
+ * SM id, 3 unused} of the last scan launch (out_host: max_warps * 8 words); returns the number of warps
+ * copied (<= max_warps) or a negative error. */
 int ngu_epi_debug_timeline(ngu_epi* h, uint64_t* out_host, int32_t max_warps);
 int ngu_epi_scan_timing_begin(ngu_epi* h, int32_t max_calls);
 int ngu_epi_scan_timing_end(ngu_epi* h, double* total_ms, int32_t* calls);

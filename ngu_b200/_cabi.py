@@ -65,6 +65,7 @@ SYMBOLS = {
     "ngu_epi_log_flush": (C.c_int, [_P, _P]),
     "ngu_epi_launch_count": (C.c_int64, [_P]),
     "ngu_epi_scan_geometry": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "ngu_epi_debug_chunk": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32)]),
     "ngu_epi_debug_timeline": (C.c_int, [_P, _P, C.c_int32]),
     "ngu_epi_scan_timing_begin": (C.c_int, [_P, C.c_int32]),
     "ngu_epi_scan_timing_end": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
@@ -91,7 +92,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the ABI is out of date
         fn.restype = res
         fn.argtypes = args
-    if lib.ngu_epi_abi_version() != 2:
+    if lib.ngu_epi_abi_version() != 3:
         raise NguEpiError("libngu_epi.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

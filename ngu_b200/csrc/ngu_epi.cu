@@ -79,6 +79,7 @@ void build_pairwise_plan(int off, int n, std::vector<int2>& plan) {
     plan.push_back(make_int2(-1, 0));
 }
 constexpr int kMinTilesPerWarp = 4;
+constexpr int kDynMinAvgTilesDefault = 24;
 
 }  // namespace
 
@@ -88,13 +89,18 @@ struct ngu_epi {
     int sm_count = 0;
     bool owns_memory = false;
     float* memory = nullptr;         // [B][N][32]
-    u64* partial = nullptr;          // [B][max_parts][k]
+    u64* cand = nullptr;             // [B][max_cand][2] epoch-tagged candidate keys of the scan kernel
     float* topk_d2 = nullptr;        // [B][k]
     int32_t* topk_idx = nullptr;     // [B][k]
     float* dist = nullptr;           // [B][k]
     double* rank_sums = nullptr;     // [2k+1]
     double* log_sums = nullptr;      // [5]
-    unsigned int* actor_arrivals = nullptr;  // [B] per-actor flush counter of the scan kernel
+    u64* actor_state = nullptr;              // [B][2] per actor {published floor, arrived tiles << 32 | reserved candidates}
+    unsigned int* sched_ctr = nullptr;       // [4] dynamic chunk counter, finished-warp counter, launch epoch
+    ScanSched sched{};
+    double sched_static_frac = 0.6;          // share of the tiles handed out statically (experiments: NGU_EPI_SCHED=frac,c2)
+    int sched_c2 = 16;                       // tiles per dynamic chunk
+    int sched_min_avg = kDynMinAvgTilesDefault;   // fair share (tiles per warp) below which the schedule is static only
     int2* plan_dev = nullptr;        // pairwise-sum plan for n = B (epilogue rank sums)
     int plan_len = 0;
     // p2p rank-sum exchange (multi-GPU): local inbox + IPC-mapped peer inboxes
@@ -105,6 +111,7 @@ struct ngu_epi {
     bool use_pdl = true;
     unsigned long long* timeline = nullptr;   // NGU_EPI_DEBUG_TIMELINE=1: per-warp timestamps of the last scan
     int debug_phase_mask = ~0;       // NGU_EPI_DEBUG_PHASES: experiments only (tools/sweep.py)
+    int debug_scan = 0;              // NGU_EPI_DEBUG_SCAN: experiments only (ScanParams::debug)
     // staging for the *_host entry points
     cudaStream_t own_stream = nullptr;
     float* q_stage_dev = nullptr;    // [B][32] followed by alpha [B]: one H2D copy per step
@@ -116,7 +123,7 @@ struct ngu_epi {
     // launch geometry
     Variant var{};
     CUtensorMap tmap{};
-    int grid = 0, tiles_per_actor = 0, tiles_per_warp = 0, max_parts = 0;
+    int grid = 0, tiles_per_actor = 0, max_cand = 0;
     int64_t total_tiles = 0;
     bool scanned = false;
     int64_t launches = 0;
@@ -163,17 +170,48 @@ int build_tensor_map(ngu_epi* h) {
     return NGU_OK;
 }
 
+// Launch geometry + chunk schedule of the scan kernel (ScanSched, scan_topk.cuh).
+//   big shapes  : one full wave; every warp gets a static chunk of `sched_static_frac` of its fair
+//                 share, the rest is handed out dynamically in chunks of c2 tiles, interleaved over the
+//                 actors of the dynamic region;
+//   small shapes: (fair share below kDynMinAvgTilesDefault tiles) static only, >= kMinTilesPerWarp tiles per
+//                 warp, grid sized to the work - these are launch-latency bound, keep the atomics out.
 void plan_geometry(ngu_epi* h) {
     const int tile_rows = 32 * h->var.rpl;
     h->tiles_per_actor = (h->cfg.capacity + tile_rows - 1) / tile_rows;
     h->total_tiles = static_cast<int64_t>(h->cfg.n_actors) * h->tiles_per_actor;
+    const int64_t T = h->total_tiles;
     const int64_t max_warps = static_cast<int64_t>(h->sm_count) * h->var.ctas_per_sm * h->var.warps;
-    int64_t tpw = (h->total_tiles + max_warps - 1) / max_warps;
-    if (tpw < kMinTilesPerWarp) tpw = kMinTilesPerWarp;
-    h->tiles_per_warp = static_cast<int>(tpw);
-    const int64_t warps_needed = (h->total_tiles + tpw - 1) / tpw;
-    h->grid = static_cast<int>((warps_needed + h->var.warps - 1) / h->var.warps);
-    h->max_parts = static_cast<int>((h->tiles_per_actor + tpw - 1) / tpw) + 1;
+    ScanSched& sc = h->sched;
+    sc = ScanSched{};
+    sc.total_tiles = static_cast<int32_t>(T);
+    sc.c2 = 1; sc.rows = 1; sc.cols = 0;
+    int min_chunk;
+    if (T < h->sched_min_avg * max_warps || h->sched_static_frac >= 1.0 || h->sched_c2 <= 0) {
+        int64_t tpw = (T + max_warps - 1) / max_warps;
+        if (tpw < kMinTilesPerWarp) tpw = kMinTilesPerWarp;
+        sc.s1 = static_cast<int32_t>(tpw);
+        sc.n1 = static_cast<int32_t>((T + tpw - 1) / tpw);
+        sc.n_chunks = sc.n1;
+        h->grid = (sc.n1 + h->var.warps - 1) / h->var.warps;
+        min_chunk = sc.s1;
+    } else {
+        h->grid = h->sm_count * h->var.ctas_per_sm;
+        const int64_t W = max_warps;
+        int64_t s1 = static_cast<int64_t>(h->sched_static_frac * static_cast<double>(T) / static_cast<double>(W));
+        const int c2 = h->sched_c2;
+        sc.n1 = s1 >= 1 ? static_cast<int32_t>(W) : 0;
+        sc.s1 = s1 >= 1 ? static_cast<int32_t>(s1) : 1;
+        const int64_t rest = T - static_cast<int64_t>(sc.n1) * sc.s1;
+        sc.c2 = c2;
+        sc.n2 = static_cast<int32_t>((rest + c2 - 1) / c2);
+        sc.cols = h->tiles_per_actor / c2 > 0 ? h->tiles_per_actor / c2 : 1;   // ~ chunks per actor
+        sc.rows = (sc.n2 + sc.cols - 1) / sc.cols;
+        min_chunk = static_cast<int>(sc.n1 > 0 && sc.s1 < c2 ? sc.s1 : c2);
+        sc.n_chunks = sc.n1 + sc.rows * sc.cols;
+    }
+    // worst case every run publishes k candidates; runs per actor <= chunks overlapping it
+    h->max_cand = ((h->tiles_per_actor + min_chunk - 1) / min_chunk + 3) * h->cfg.k;
 }
 
 int default_state(ngu_epi* h) {
@@ -255,12 +293,20 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
     if (const char* e = getenv("NGU_EPI_PDL")) h->use_pdl = atoi(e) != 0;
     if (const char* e = getenv("NGU_EPI_DEBUG_TIMELINE")) {
         if (atoi(e) != 0) {
-            const size_t n = static_cast<size_t>(prop.multiProcessorCount) * 4 * 32 * 4;   // >= max warps * 4
+            const size_t n = static_cast<size_t>(prop.multiProcessorCount) * 4 * 32 * 8;   // >= max warps * 8
             CREATE_TRY(cudaMalloc(&h->timeline, n * sizeof(unsigned long long)));
             CREATE_TRY(cudaMemset(h->timeline, 0, n * sizeof(unsigned long long)));
         }
     }
     if (const char* e = getenv("NGU_EPI_DEBUG_PHASES")) h->debug_phase_mask = atoi(e);
+    if (const char* e = getenv("NGU_EPI_DEBUG_SCAN")) h->debug_scan = atoi(e);
+    if (const char* e = getenv("NGU_EPI_SCHED")) {   // experiments and tests: "static_frac,c2[,min_avg_tiles]"
+        double f = 0.6; int c2 = 16, mn = kDynMinAvgTilesDefault;
+        const int got = sscanf(e, "%lf,%d,%d", &f, &c2, &mn);
+        if (got >= 1 && f >= 0.0) h->sched_static_frac = f;
+        if (got >= 2) h->sched_c2 = c2;
+        if (got >= 3 && mn >= 0) h->sched_min_avg = mn;
+    }
     plan_geometry(h);
 
     const int B = cfg->n_actors, k = cfg->k;
@@ -272,14 +318,25 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
         h->owns_memory = true;
         CREATE_TRY(cudaMemset(h->memory, 0, mem_bytes));                 // torch.zeros, episodic_novelty.py:32
     }
-    CREATE_TRY(cudaMalloc(&h->partial, static_cast<size_t>(B) * h->max_parts * k * sizeof(u64)));
+    {   // epoch-tagged candidates: zeroed once (tag 0 is never valid), 16 bytes per entry
+        const size_t cbytes = static_cast<size_t>(B) * h->max_cand * 2 * sizeof(u64);
+        CREATE_TRY(cudaMalloc(&h->cand, cbytes));
+        CREATE_TRY(cudaMemset(h->cand, 0, cbytes));
+    }
     CREATE_TRY(cudaMalloc(&h->topk_d2, static_cast<size_t>(B) * k * sizeof(float)));
     CREATE_TRY(cudaMalloc(&h->topk_idx, static_cast<size_t>(B) * k * sizeof(int32_t)));
     CREATE_TRY(cudaMalloc(&h->dist, static_cast<size_t>(B) * k * sizeof(float)));
     CREATE_TRY(cudaMalloc(&h->rank_sums, NGU_EPI_RANK_SUMS(NGU_EPI_MAX_K) * sizeof(double)));
     CREATE_TRY(cudaMalloc(&h->log_sums, 8 * sizeof(double)));
-    CREATE_TRY(cudaMalloc(&h->actor_arrivals, static_cast<size_t>(B) * sizeof(unsigned int)));
-    CREATE_TRY(cudaMemset(h->actor_arrivals, 0, static_cast<size_t>(B) * sizeof(unsigned int)));
+    CREATE_TRY(cudaMalloc(&h->actor_state, static_cast<size_t>(B) * 2 * sizeof(u64)));
+    CREATE_TRY(cudaMemset(h->actor_state, 0, static_cast<size_t>(B) * 2 * sizeof(u64)));
+    CREATE_TRY(cudaMalloc(&h->sched_ctr, 4 * sizeof(unsigned int)));
+    {
+        unsigned int init[4] = {0u, 0u, 1u, 0u};         // first launch epoch = 1
+        if (const char* e = getenv("NGU_EPI_DEBUG_EPOCH")) init[2] = static_cast<unsigned int>(strtoul(e, nullptr, 0));   // tests: cross the wrap
+        if (init[2] == 0u) init[2] = 1u;
+        CREATE_TRY(cudaMemcpy(h->sched_ctr, init, sizeof init, cudaMemcpyHostToDevice));
+    }
     CREATE_TRY(cudaMalloc(&h->state, sizeof(DevState)));
     CREATE_TRY(cudaMemset(h->state, 0, sizeof(DevState)));
     {
@@ -327,8 +384,8 @@ void ngu_epi_destroy(ngu_epi* h) {
             if (g != h->p2p.rank && h->p2p.peer[g]) cudaIpcCloseMemHandle(h->p2p.peer[g]);
     cudaFree(h->inbox);
     if (h->owns_memory) cudaFree(h->memory);
-    cudaFree(h->partial); cudaFree(h->topk_d2); cudaFree(h->topk_idx); cudaFree(h->dist);
-    cudaFree(h->rank_sums); cudaFree(h->log_sums); cudaFree(h->state); cudaFree(h->actor_arrivals); cudaFree(h->plan_dev); cudaFree(h->timeline);
+    cudaFree(h->cand); cudaFree(h->topk_d2); cudaFree(h->topk_idx); cudaFree(h->dist);
+    cudaFree(h->rank_sums); cudaFree(h->log_sums); cudaFree(h->state); cudaFree(h->actor_state); cudaFree(h->sched_ctr); cudaFree(h->plan_dev); cudaFree(h->timeline);
     cudaFree(h->q_stage_dev); cudaFree(h->done_stage_dev);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->r_mapped) cudaFreeHost(h->r_mapped);
@@ -360,15 +417,19 @@ static cudaError_t launch_pdl(const void* fn, dim3 grid, dim3 block, size_t smem
 }
 
 static int launch_scan(ngu_epi* h, const float* q_dev, cudaStream_t s) {
+    if (reinterpret_cast<uintptr_t>(q_dev) & 15u)   // the scan fetches query rows with 16-byte bulk copies
+        return fail(h, NGU_EINVAL, "q_dev must be 16-byte aligned");
     ScanParams sp{};
-    sp.q = q_dev; sp.partial = h->partial;
+    sp.q = q_dev; sp.cand = h->cand;
     sp.n_actors = h->cfg.n_actors; sp.capacity = h->cfg.capacity; sp.k = h->cfg.k;
     sp.largest = h->consts.largest; sp.sqrt_dist = h->consts.sqrt_dist;
-    sp.tiles_per_actor = h->tiles_per_actor; sp.tiles_per_warp = h->tiles_per_warp;
-    sp.max_parts = h->max_parts; sp.total_tiles = h->total_tiles;
-    sp.actor_arrivals = h->actor_arrivals;
+    sp.tiles_per_actor = h->tiles_per_actor;
+    sp.max_cand = h->max_cand; sp.sched = h->sched; sp.sched_ctr = h->sched_ctr;
+    sp.actor_state = h->actor_state;
+    sp.timeouts = reinterpret_cast<unsigned long long*>(&h->state->exchange_timeouts);
     sp.topk_d2 = h->topk_d2; sp.topk_idx = h->topk_idx; sp.dist = h->dist;
     sp.timeline = h->timeline;
+    sp.debug = h->debug_scan;
     void* args[] = {&h->tmap, &sp};
     const bool timed = h->t_used < h->t_beg.size();
     if (timed) CU_TRY(h, cudaEventRecord(h->t_beg[h->t_used], s));
@@ -670,11 +731,21 @@ int ngu_epi_debug_timeline(ngu_epi* h, uint64_t* out_host, int32_t max_warps) {
     if (!h->timeline) return fail(h, NGU_ESTATE, "create the handle with NGU_EPI_DEBUG_TIMELINE=1");
     int rc = bind_device(h);
     if (rc) return rc;
-    const int warps = h->grid * h->var.warps;
+    int warps = h->grid * h->var.warps;
+    if (warps > h->sched.n_chunks) warps = h->sched.n_chunks;
     const int n = warps < max_warps ? warps : max_warps;
     CU_TRY(h, cudaDeviceSynchronize());
-    CU_TRY(h, cudaMemcpy(out_host, h->timeline, static_cast<size_t>(n) * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CU_TRY(h, cudaMemcpy(out_host, h->timeline, static_cast<size_t>(n) * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return n;
+}
+
+int ngu_epi_debug_chunk(const ngu_epi* h, int32_t idx, int32_t out[2]) {
+    if (!h || !out) return NGU_EINVAL;
+    if (idx < 0 || idx >= h->sched.n_chunks) return NGU_EINVAL;
+    int t = 0, te = 0;
+    chunk_range(h->sched, idx, t, te);
+    out[0] = t; out[1] = te;
+    return NGU_OK;
 }
 
 int64_t ngu_epi_launch_count(const ngu_epi* h) { return h ? h->launches : 0; }
@@ -716,10 +787,11 @@ int ngu_epi_scan_timing_end(ngu_epi* h, double* total_ms, int32_t* calls) {
     return NGU_OK;
 }
 
-int ngu_epi_scan_geometry(const ngu_epi* h, int32_t out[6]) {
+int ngu_epi_scan_geometry(const ngu_epi* h, int32_t out[8]) {
     if (!h || !out) return NGU_EINVAL;
     out[0] = h->grid; out[1] = h->var.warps * 32; out[2] = h->var.smem;
-    out[3] = h->tiles_per_warp; out[4] = h->var.stages; out[5] = 32 * h->var.rpl;
+    out[3] = h->sched.s1; out[4] = h->var.stages; out[5] = 32 * h->var.rpl;
+    out[6] = h->sched.n_chunks > h->sched.n1 ? h->sched.c2 : 0; out[7] = h->sched.n_chunks;
     return NGU_OK;
 }
 

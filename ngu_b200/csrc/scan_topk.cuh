@@ -21,12 +21,21 @@
 //     reproduce torch-CPU's exact add order (below) without any shuffles.
 //   * the query (32 floats) stays in registers for the whole actor segment;
 //     the running k-th-best threshold is a warp-uniform register (WarpTopK).
-//   * work = B * ceil(N / TILE_ROWS) tiles, cut into equal contiguous chunks of
-//     `tiles_per_warp`; a warp that crosses an actor boundary flushes its list
-//     and starts a new one.  Partial lists go to partial[B][max_parts][k]; the
-//     LAST warp to flush a given actor (per-actor arrival counter) merges that
-//     actor's partial lists in-kernel and writes the final k-NN (d^2, slot, dist),
-//     so no separate merge launch sits on the step's critical path.
+//   * work = B * ceil(N / TILE_ROWS) tiles in one linear tile space, cut into chunks by a
+//     closed-form schedule (ScanSched): every warp owns one big STATIC chunk (~60 % of its
+//     fair share, no atomics), the rest is handed out DYNAMICALLY in small chunks from a
+//     global counter.  Under saturation the HBM/L2 system serves the SMs unevenly (measured:
+//     the same TPC pairs finish a fixed share 35 % earlier than others, tools/scan_timeline.py),
+//     so equal static shares leave the kernel waiting for its slowest SMs while the rest idle;
+//     with the dynamic tail every SM pulls until the memory is exhausted.  Lane 0 is the
+//     producer: it walks the warp's chunks and records (actor, tile) of what it loaded into
+//     each ring stage in a per-stage descriptor; the consumer flushes its list whenever the
+//     actor changes.  A flush is ONE 64-bit atomic that reserves room in the actor's candidate
+//     buffer and counts the tiles that have arrived; the candidates are published without a
+//     fence as epoch-tagged words (see "partial results" below).  When a warp has streamed
+//     its last tile it takes merge jobs (one actor each) and merges that actor's candidates
+//     incrementally, as they are published, into the final k-NN (d^2, slot, dist): the merges
+//     overlap the end of the stream, and no separate merge launch sits on the critical path.
 //   * programmatic dependent launch: the kernel lets its dependent (the epilogue
 //     kernel) get resident immediately and itself waits on its predecessor only
 //     right before the first TMA load (griddepcontrol).
@@ -43,23 +52,64 @@
 
 namespace ngu {
 
+// Chunk index -> tile range, closed form (no table, no dependent load after the counter atomic):
+//   chunks [0, n1)   s1 tiles each, tiles [0, n1*s1): chunk idx == global warp idx, taken statically;
+//   chunks [n1, ...) the remaining tiles, cut into n2 "natural" chunks of c2 tiles that form a matrix
+//                    of `rows` x `cols` (row ~ actor, cols ~ chunks per actor), handed out dynamically
+//                    COLUMN BY COLUMN: consecutive handouts belong to different actors and every actor
+//                    of the dynamic region is worked on during the whole dynamic phase, so later runs
+//                    of an actor start from the floor its earlier runs have published (few candidates)
+//                    and the merges of those actors proceed in parallel on different warps.
+// Every chunk index below the number of launched warps is taken statically by that warp; the
+// dynamic counter hands out the indices above.  Indices whose natural chunk is >= n2 are empty.
+// (Measured on B200, 256 x 30k: s1 = 60 % of the fair share and c2 = 16 tiles; smaller chunks pay
+// more in flushes than they win at the ragged end, and tapering the last chunks did not pay either.)
+struct ScanSched {
+    int32_t total_tiles;     // B * tiles_per_actor
+    int32_t n_chunks;        // n1 + rows * cols
+    int32_t n1, s1;
+    int32_t n2, c2;
+    int32_t rows, cols;
+};
+
+__host__ __device__ __forceinline__ void chunk_range(const ScanSched& s, int idx, int& t, int& te) {
+    if (idx < s.n1) {
+        t = idx * s.s1;
+        te = t + s.s1;
+    } else {
+        const int i = idx - s.n1;
+        const int c = i / s.rows;
+        const int j = (i - c * s.rows) * s.cols + c;
+        if (j >= s.n2) { t = 0; te = 0; return; }
+        t = s.n1 * s.s1 + j * s.c2;
+        te = t + s.c2;
+    }
+    if (te > s.total_tiles) te = s.total_tiles;
+}
+
 struct ScanParams {
     const float* q;          // [B][32]
-    u64* partial;            // [B][max_parts][k]
+    u64* cand;               // [B][max_cand][2] epoch-tagged candidate keys (see "partial results")
     int32_t n_actors;        // B
     int32_t capacity;        // N
     int32_t k;
     int32_t largest;         // 1 = reference mode (farthest), 0 = paper (nearest)
     int32_t tiles_per_actor; // ceil(N / TILE_ROWS)
-    int32_t tiles_per_warp;  // chunk length
-    int32_t max_parts;       // partial lists reserved per actor
+    int32_t max_cand;        // candidate entries reserved per actor (worst case: every run publishes k)
     int32_t sqrt_dist;       // 1: dist = sqrt(d2) (reference), 0: dist = d2 (paper)
-    int64_t total_tiles;     // B * tiles_per_actor
-    unsigned int* actor_arrivals;  // [B] zero between launches
+    ScanSched sched;
+    unsigned int* sched_ctr;       // [0] dynamic chunk counter, [1] finished warps, [3] merge-job counter (zero between
+                                   // launches), [2] launch epoch = tag of this launch's candidates and floors (never 0)
+    unsigned long long* timeouts;  // incremented if a merge gave up waiting for a candidate (must stay 0)
+    u64* actor_state;              // [B][2]: {floor, ctr} (16 bytes, so that one bulk copy can fetch the floor)
+                                   //   floor: epoch << 32 | hi word of a key known to be <= the final k-th best
+                                   //   ctr  : hi32 tiles arrived, lo32 candidates reserved; zero between launches
     float* topk_d2;          // [B][k]
     int32_t* topk_idx;       // [B][k]
     float* dist;             // [B][k]
-    unsigned long long* timeline;  // debug (tools/scan_timeline.py): per warp {start, first tile, scan end, flush end} ns, or null
+    unsigned long long* timeline;  // debug (tools/scan_timeline.py): per warp {start, first tile, scan end, flush end, smid} (8 words), or null
+    int32_t debug;           // experiments only (NGU_EPI_DEBUG_SCAN): 1 = no top-k offers, 2 = no distance math, 4 = no flush,
+                             // 8 = no merge, 16 = no floor seeding
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -68,75 +118,165 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
-// Release-only arrival.  Deliberately not __threadfence() + atomicAdd: __threadfence() compiles to
-// MEMBAR.SC.GPU + CCTL.IVALL (a sequentially consistent fence plus an L1 invalidate); the release
-// form is MEMBAR.ALL.GPU + ATOMG and is all the writer side needs.
-__device__ __forceinline__ unsigned atom_add_release_gpu(unsigned* addr, unsigned v) {
-    unsigned old;
-    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;"
-                 : "=r"(old) : "l"(__cvta_generic_to_global(addr)), "r"(v) : "memory");
-    return old;
-}
-
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// Final k-NN of one actor from the warp-resident list.
-__device__ __forceinline__ void write_knn(const ScanParams& p, int actor, const WarpTopK& top, int lane) {
-    if (lane < p.k) {
-        const bool largest = p.largest != 0;
-        const float d2 = key_d2(top.lkey, largest);
-        const int64_t o = static_cast<int64_t>(actor) * p.k + lane;
-        p.topk_d2[o] = d2;
-        p.topk_idx[o] = key_slot(top.lkey);
-        p.dist[o] = p.sqrt_dist ? __fsqrt_rn(d2) : d2;   // episodic_novelty.py:52 .sqrt(), winners only
+struct KnnOut { float* d2; int32_t* idx; float* dist; };   // one actor's [k] outputs
+
+// Final k-NN of one actor from a warp-resident list.  flags: 1 = largest, 2 = sqrt.
+__device__ __forceinline__ void write_knn(KnnOut out, int k, int flags, u64 lkey, int lane) {
+    if (lane < k) {
+        const float d2 = key_d2(lkey, (flags & 1) != 0);
+        out.d2[lane] = d2;
+        out.idx[lane] = key_slot(lkey);
+        out.dist[lane] = (flags & 2) ? __fsqrt_rn(d2) : d2;   // episodic_novelty.py:52 .sqrt(), winners only
     }
 }
+__device__ __forceinline__ KnnOut knn_out(const ScanParams& p, int actor) {
+    const int64_t o = static_cast<int64_t>(actor) * p.k;
+    return KnnOut{p.topk_d2 + o, p.topk_idx + o, p.dist + o};
+}
+__device__ __forceinline__ int knn_flags(const ScanParams& p) { return (p.largest ? 1 : 0) | (p.sqrt_dist ? 2 : 0); }
+__device__ __forceinline__ u64* actor_floor(const ScanParams& p, int actor) { return p.actor_state + 2 * static_cast<int64_t>(actor); }
+__device__ __forceinline__ u64* actor_ctr(const ScanParams& p, int actor) { return p.actor_state + 2 * static_cast<int64_t>(actor) + 1; }
 
-// Called by a whole warp when it has finished its share of `actor`.
-__device__ __forceinline__ void flush_actor(const ScanParams& p, int actor, int64_t gw, WarpTopK& top, int lane) {
-    const int64_t t0 = static_cast<int64_t>(actor) * p.tiles_per_actor;
-    const int first = static_cast<int>(t0 / p.tiles_per_warp);
-    const int last = static_cast<int>((t0 + p.tiles_per_actor - 1) / p.tiles_per_warp);
-    const int nparts = last - first + 1;
-    if (nparts == 1) {           // this warp scanned the whole actor
-        write_knn(p, actor, top, lane);
-        return;
-    }
-    const int k = p.k;
-    u64* base = p.partial + static_cast<int64_t>(actor) * p.max_parts * k;
-    if (lane < k) base[(gw - first) * k + lane] = top.lkey;
-    __syncwarp();    // orders every lane's list store before lane 0's release below
-    unsigned prev = 0;
-    if (lane == 0) prev = atom_add_release_gpu(p.actor_arrivals + actor, 1u);
-    prev = __shfl_sync(kFull, prev, 0);
-    if (prev != static_cast<unsigned>(nparts - 1)) return;
-    // last arrival: every partial list of this actor is in L2 (acquire side: one full fence, B times per launch)
-    __threadfence();
-    if (lane == 0) p.actor_arrivals[actor] = 0;   // re-arm for the next launch
-    // Pass 1: every partial list that is full proves "k keys >= its k-th entry exist", so the largest
-    // of those k-th entries T is a lower bound of the final k-th best key.  Seeding the merge with it
-    // (floor = T-1: keys are integers and T itself must stay eligible) leaves only a few dozen real
-    // candidates however many lists there are, instead of sorting all nparts*k keys.
-    u64 T = 0ull;
-    for (int l = lane; l < nparts; l += 32) T = umax64(T, __ldcg(base + l * k + (k - 1)));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) T = umax64(T, __shfl_xor_sync(kFull, T, o));
-    WarpTopK m;
-    m.reset(T ? T - 1ull : 0ull);
-    // Pass 2: offer all keys, four independent loads in flight per lane.
-    const int nkeys = nparts * k;
-    for (int i0 = 0; i0 < nkeys; i0 += 128) {
-        u64 key[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + 32 * u + lane;
-            key[u] = i < nkeys ? __ldcg(base + i) : 0ull;
+// ---- partial results: fence-free, compacted, seeded ------------------------------------------------
+// A run = the consecutive tiles of one actor that one warp scanned with one list.  With dynamic chunks
+// an actor is covered by up to ~120 runs, so publishing and merging them must cost next to nothing:
+//   * no fences.  A release fence (MEMBAR.ALL.GPU) in the middle of the stream waits for the warp's
+//     in-flight TMA tiles and drains its pipeline (~9 us per flush, measured).  Instead every candidate
+//     is written as two 8-byte words that each carry the launch epoch in their low half
+//     (w0 = key.hi << 32 | tag, w1 = key.lo << 32 | tag; 8-byte stores are single-copy atomic), and the
+//     merging warp polls the entries it is owed until both tags match - the LL protocol of NCCL.
+//   * one atomic per flush.  actor_ctr[b] += tiles << 32 | n  both reserves n candidate slots (low
+//     half of the return value = position) and counts arrived tiles (high half): when the tile count
+//     is complete the low half is the number of candidates to merge.
+//   * nobody waits for that atomic.  Its return value is first looked at after the NEXT tile has been
+//     processed (complete_pending); the flushed list waits in two registers per lane meanwhile.
+//   * floors.  A full list proves that its k-th key is <= the final k-th best; the hi word of the best
+//     such proof is kept per actor (atomicMax, epoch in the high half so stale values lose).  A run
+//     starts from it and keeps only keys above it, so late runs publish few or no candidates and the
+//     merge reads a few hundred entries in ONE round trip instead of runs*k in many.
+//   * nobody waits at a run start either.  The query row and the actor's floor are fetched by the
+//     producer lane with two small bulk copies that complete on the SAME mbarrier as the run's first
+//     tile (three tiles ahead of the consumer), instead of loads whose L2 latency under a saturated
+//     memory system (1-2 us) the consumer would sit out.
+__device__ __forceinline__ void st_ll(u64* dst, u64 key, uint32_t tag) {
+    const u64 w0 = (key & 0xFFFFFFFF00000000ull) | tag;
+    const u64 w1 = (key << 32) | tag;
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ bool ld_ll(const u64* src, uint32_t tag, u64& key) {
+    u64 w0, w1;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+    key = (w0 & 0xFFFFFFFF00000000ull) | (w1 >> 32);
+    return static_cast<uint32_t>(w0) == tag && static_cast<uint32_t>(w1) == tag;
+}
+__device__ __forceinline__ u64 ld_volatile_u64(const u64* src) {
+    u64 v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+    return v;
+}
+constexpr int kLLSpinLimit = 1 << 22;   // ~ seconds; a healthy wait is about one tile time
+__device__ __forceinline__ u64 wait_ll(unsigned long long* timeouts, const u64* src, uint32_t tag) {
+    u64 key;
+    int spins = 0;
+    while (!ld_ll(src, tag, key)) {
+        if (++spins > kLLSpinLimit) {
+            atomicAdd(timeouts, 1ull);
+            return 0ull;
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) m.offer(key[u], lane, k);
     }
-    write_knn(p, actor, m, lane);
+    return key;
+}
+// floor word -> the largest key that is certainly NOT needed (0 = no floor)
+__device__ __forceinline__ u64 floor_key(u64 floor_word, uint32_t tag) {
+    const uint32_t hi = static_cast<uint32_t>(floor_word);
+    if (static_cast<uint32_t>(floor_word >> 32) != tag || hi == 0u) return 0ull;
+    return (static_cast<u64>(hi) << 32) - 1ull;   // every key whose hi word is >= hi stays eligible
+}
+
+// A run of `run_tiles` tiles of `actor` ends (whole warp).  Returns true if a publication is pending:
+// then pend_key (per lane) / pend_n hold the candidates and pend_ret (lane 0) the UNREAD result of the
+// reserve+arrive atomic.
+constexpr uint32_t kWrittenDirectly = 0xFFFFFFFFu;   // actor_ctr low word: the k-NN is already final
+__device__ __forceinline__ bool flush_run(const ScanParams& p, int actor, int run_tiles, uint32_t tag, const WarpTopK& top,
+                                          int lane, u64& pend_key, int& pend_n, u64& pend_ret) {
+    const int k = p.k;
+    if (run_tiles == p.tiles_per_actor) {           // this warp scanned the whole actor: no merge needed
+        write_knn(knn_out(p, actor), k, knn_flags(p), top.lkey, lane);
+        if (lane == 0)
+            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(actor_ctr(p, actor)),
+                         "l"((static_cast<u64>(run_tiles) << 32) | kWrittenDirectly) : "memory");
+        return false;
+    }
+    const bool have = lane < k && top.lkey != 0ull;
+    pend_key = have ? top.lkey : 0ull;
+    pend_n = __popc(__ballot_sync(kFull, have));    // the real keys are a prefix of the lanes
+    if (pend_n == k && lane == k - 1)               // full list: its k-th key bounds the final k-th best from below
+        atomicMax(actor_floor(p, actor), (static_cast<u64>(tag) << 32) | (top.lkey >> 32));
+    if (lane == 0)
+        pend_ret = atomicAdd(actor_ctr(p, actor), (static_cast<u64>(run_tiles) << 32) | static_cast<u64>(pend_n));
+    return true;
+}
+
+// One tile later: the atomic has come back; publish the candidates at the reserved position.
+__device__ __forceinline__ void complete_pending(const ScanParams& p, int actor, u64 pend_key, int pend_n, u64 pend_ret,
+                                                 uint32_t tag, int lane) {
+    const unsigned pos = static_cast<unsigned>(__shfl_sync(kFull, pend_ret, 0));
+    u64* cand = p.cand + static_cast<int64_t>(actor) * p.max_cand * 2;
+    if (lane < pend_n) st_ll(cand + (pos + lane) * 2, pend_key, tag);
+}
+
+// When a warp has streamed its last tile it takes merge jobs (one actor each) from a global counter
+// until none are left.  Warps finish up to ~20 us apart, so the jobs are picked up by the early
+// finishers while the rest still stream, and a job is worked INCREMENTALLY: the warp consumes the
+// actor's candidates as they are published (the low half of the actor's counter says how many are
+// reserved, the tags say which have landed) and keeps the running top-k in registers; when the tile
+// count finally completes, only the last few candidates are left to read - one round trip after the
+// last tile instead of a whole merge.  Nothing is merged inside the streaming loop, so the loop
+// carries no merge registers.
+__device__ __forceinline__ void merge_job(const ScanParams& p, int actor, uint32_t tag, int lane,
+                                          unsigned long long* tl /* debug timeline record or null */) {
+    const int k = p.k;
+    u64* ctr = actor_ctr(p, actor);
+    const u64* cand = p.cand + static_cast<int64_t>(actor) * p.max_cand * 2;
+    WarpTopK m;
+    // any floor published during this launch is a valid lower bound of the final k-th best
+    m.reset(floor_key(ld_volatile_u64(actor_floor(p, actor)), tag));
+    int done = 0, spins = 0;
+    uint32_t n = 0;
+    for (;;) {
+        const u64 c = ld_volatile_u64(ctr);
+        const bool complete = static_cast<uint32_t>(c >> 32) == static_cast<uint32_t>(p.tiles_per_actor);
+        n = static_cast<uint32_t>(c);
+        if (n == kWrittenDirectly) break;                 // (only ever set together with the full tile count)
+        const int avail = static_cast<int>(n);
+        while (done < avail) {                            // eight independent loads in flight per lane
+            u64 key[8];
+            unsigned okm = 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = done + 32 * u + lane;
+                key[u] = 0ull;
+                if (i >= avail || ld_ll(cand + i * 2, tag, key[u])) okm |= 1u << u;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (!((okm >> u) & 1u)) key[u] = wait_ll(p.timeouts, cand + (done + 32 * u + lane) * 2, tag);
+                m.offer(key[u], lane, k);
+            }
+            done += 256;
+        }
+        done = avail;
+        if (complete) break;
+        if (++spins > kLLSpinLimit) { if (lane == 0) atomicAdd(p.timeouts, 1ull); break; }
+    }
+    __syncwarp();
+    if (lane == 0) *ctr = 0ull;                           // re-arm for the next launch: every arrival has been performed
+    if (tl && lane == 0) { tl[6] = n; tl[7] = globaltimer_ns(); }
+    if (n == kWrittenDirectly || (p.debug & 8)) return;
+    write_knn(knn_out(p, actor), k, knn_flags(p), m.lkey, lane);
 }
 
 // ---- PTX wrappers ---------------------------------------------------------
@@ -178,6 +318,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
         "l"(map), "r"(c0), "r"(c1), "r"(bar), "l"(policy)
         : "memory");
+}
+// plain (1-D) bulk copy global -> shared, completing on an mbarrier; 16-byte granularity
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
 }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
@@ -226,12 +372,16 @@ struct ScanCfg {
     static constexpr int kTileRows = 32 * RPL;
     static constexpr int kTileBytes = kTileRows * 128;
     static constexpr int kThreads = WARPS * 32;
-    // tiles + 1024 B alignment slack + barriers
-    static constexpr int kSmemBytes = WARPS * STAGES * kTileBytes + 1024 + WARPS * STAGES * 8;
+    static constexpr int kAuxBytes = 128 + 16;   // per stage: query row + {floor, ctr} of the actor whose run starts there
+    // tiles + 1024 B alignment slack + barriers + per-stage descriptors + per-stage run-start data
+    static constexpr int kSmemBytes = WARPS * STAGES * kTileBytes + 1024 + WARPS * STAGES * (16 + kAuxBytes);
+    // CTAs per SM the shared memory allows (227 KB per SM): tells ptxas how many registers it may use.
+    // Without it ptxas squeezes the kernel into 80 registers and spills producer state in the hot loop.
+    static constexpr int kMaxCtasPerSm = (227 * 1024) / (kSmemBytes + 1024) > 0 ? (227 * 1024) / (kSmemBytes + 1024) : 1;
 };
 
 template <int WARPS, int STAGES, int RPL>
-__global__ void __launch_bounds__(WARPS * 32) scan_topk_kernel(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxCtasPerSm) scan_topk_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                 const ScanParams p) {
     using Cfg = ScanCfg<WARPS, STAGES, RPL>;
     extern __shared__ uint8_t smem_raw[];
@@ -242,17 +392,20 @@ __global__ void __launch_bounds__(WARPS * 32) scan_topk_kernel(const __grid_cons
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles0 = (raw + 1023u) & ~1023u;
     const uint32_t bars0 = tiles0 + WARPS * STAGES * Cfg::kTileBytes;
+    const uint32_t desc0 = bars0 + WARPS * STAGES * 8;
     const uint32_t my_tiles = tiles0 + warp * STAGES * Cfg::kTileBytes;
     const uint32_t my_bars = bars0 + warp * STAGES * 8;
+    const uint32_t my_desc = desc0 + warp * STAGES * 8;   // per stage {actor, tile in actor}; actor < 0: no more work
+    const uint32_t aux0 = desc0 + WARPS * STAGES * 8;     // 16-byte aligned: everything before it is a multiple of 16
+    const uint32_t my_aux = aux0 + warp * STAGES * Cfg::kAuxBytes;
 
     pdl_launch_dependents();   // the epilogue kernel may become resident now; it waits on us
-    const int64_t gw = static_cast<int64_t>(blockIdx.x) * WARPS + warp;
+    const int gw = blockIdx.x * WARPS + warp;
+    const int n_warps = gridDim.x * WARPS;
     const unsigned long long tl0 = p.timeline ? globaltimer_ns() : 0ull;
     unsigned long long tl1 = 0ull;
-    const int64_t t_begin = gw * p.tiles_per_warp;
-    int64_t t_end = t_begin + p.tiles_per_warp;
-    if (t_end > p.total_tiles) t_end = p.total_tiles;
-    if (t_begin >= t_end) return;  // whole warp exits together; no CTA-wide barriers below
+    const ScanSched& sc = p.sched;
+    if (gw >= sc.n_chunks) return;  // whole warp exits together; no CTA-wide barriers below
 
     if (lane == 0) {
 #pragma unroll
@@ -265,81 +418,161 @@ __global__ void __launch_bounds__(WARPS * 32) scan_topk_kernel(const __grid_cons
 
     const int tpa = p.tiles_per_actor;
     const int N = p.capacity;
-    int b = static_cast<int>(t_begin / tpa);          // actor of the current tile
-    int ti = static_cast<int>(t_begin - static_cast<int64_t>(b) * tpa);  // tile index inside the actor
-
-    // Prologue: fill the ring.  (Producer cursor runs STAGES tiles ahead.)
     const uint64_t policy = l2_evict_first_policy();
-    int pb = b, pti = ti;
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) {
-            if (t_begin + s < t_end) {
-                const uint32_t bar = my_bars + 8 * s;
-                mbar_expect_tx(bar, Cfg::kTileBytes);
-                tma_load_2d(my_tiles + s * Cfg::kTileBytes, &tmap, 0,
-                            pb * N + pti * Cfg::kTileRows, bar, policy);
-                if (++pti == tpa) { pti = 0; ++pb; }
+    const uint32_t tag = __ldcg(p.sched_ctr + 2);   // launch epoch (first needed at the first flush)
+
+    // ---- producer (lane 0): walks this warp's chunks STAGES tiles ahead of the consumer ----
+    int pt, pte;                       // current chunk: next tile to load, end
+    chunk_range(sc, gw, pt, pte);      // first chunk is static: no atomic before the first load
+    int pb = pt / tpa;                 // actor / tile-in-actor of `pt`
+    int pti = pt - pb * tpa;
+    int pending = sc.n_chunks;         // next chunk index, fetched one chunk ahead
+    int last_pb = -1;                  // actor of the tile issued last: a change = the consumer starts a new run there
+    bool live = true;
+    if (lane == 0 && n_warps < sc.n_chunks) pending = n_warps + static_cast<int>(atomicAdd(p.sched_ctr, 1u));
+    auto produce = [&](int s) {        // lane 0 only
+        while (live && pt == pte) {
+            if (pending < sc.n_chunks) {
+                chunk_range(sc, pending, pt, pte);
+                pb = pt / tpa;
+                pti = pt - pb * tpa;
+                pending = n_warps + static_cast<int>(atomicAdd(p.sched_ctr, 1u));
+            } else {
+                live = false;
             }
         }
+        const uint32_t dsc = my_desc + 8 * s;
+        if (live) {
+            asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(dsc), "r"(pb), "r"(pti) : "memory");
+            const uint32_t bar = my_bars + 8 * s;
+            const bool run_start = pb != last_pb;
+            mbar_expect_tx(bar, Cfg::kTileBytes + (run_start ? Cfg::kAuxBytes : 0));
+            tma_load_2d(my_tiles + s * Cfg::kTileBytes, &tmap, 0, pb * N + pti * Cfg::kTileRows, bar, policy);
+            if (run_start) {           // the run's query row and floor travel with its first tile
+                const uint32_t aux = my_aux + s * Cfg::kAuxBytes;
+                bulk_load(aux, p.q + static_cast<int64_t>(pb) * 32, 128, bar);
+                bulk_load(aux + 128, actor_floor(p, pb), 16, bar);
+                last_pb = pb;
+            }
+            ++pt;
+            if (++pti == tpa) { pti = 0; ++pb; }
+        } else {
+            asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(dsc), "r"(-1), "r"(0) : "memory");
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) produce(s);
     }
+    __syncwarp();
 
     const bool largest = p.largest != 0;
     const int k = p.k;
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     float q[32];
     WarpTopK top;
-    int cur = -1;    // actor whose list is being built
+    int cur = -1;        // actor whose list is being built
+    int run_tiles = 0;   // tiles of `cur` in the list
+    bool run_start = false;     // the tile being consumed is the first of a run
+    int pend_actor = -1, pend_n = 0;   // flushed run whose reserve/arrive atomic has not been read yet
+    u64 pend_key = 0ull, pend_ret = 0ull;
     int stage = 0;
     uint32_t parity = 0;
+    bool first = true;
 
-    for (int64_t t = t_begin; t < t_end; ++t) {
+    for (;;) {
+        int b, ti;
+        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(b), "=r"(ti) : "r"(my_desc + 8 * stage) : "memory");
+        if (b < 0) break;
         if (b != cur) {
-            if (cur >= 0) flush_actor(p, cur, gw, top, lane);
-            cur = b;
-            top.reset();
-            const float4* qv = reinterpret_cast<const float4*>(p.q + static_cast<int64_t>(b) * 32);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 v = __ldg(qv + c);
-                q[4 * c + 0] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w;
+            if (cur >= 0 && !(p.debug & 4)) {
+                if (pend_actor >= 0) complete_pending(p, pend_actor, pend_key, pend_n, pend_ret, tag, lane);
+                pend_actor = flush_run(p, cur, run_tiles, tag, top, lane, pend_key, pend_n, pend_ret) ? cur : -1;
             }
+            cur = b;
+            run_tiles = 0;
+            run_start = true;
         }
 
         mbar_wait(my_bars + 8 * stage, parity);
-        if (p.timeline && t == t_begin) tl1 = globaltimer_ns();
+        if (p.timeline && first) { tl1 = globaltimer_ns(); first = false; }
+        if (run_start) {   // query row and floor arrived with the tile (same mbarrier)
+            const uint32_t aux = my_aux + stage * Cfg::kAuxBytes;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 v = lds128(aux + 16 * c);
+                q[4 * c + 0] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w;
+            }
+            u64 fw;
+            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(fw) : "r"(aux + 128) : "memory");
+            // keys at or below the actor's published floor cannot make the final top-k
+            top.reset((p.debug & 16) ? 0ull : floor_key(fw, tag));
+            run_start = false;
+        }
         const uint32_t tile = my_tiles + stage * Cfg::kTileBytes;
         const int row0 = ti * Cfg::kTileRows;
         float d2[RPL];
+        if (p.debug & 2) {
 #pragma unroll
-        for (int i = 0; i < RPL; ++i)
-            d2[i] = row_d2(tile + static_cast<uint32_t>(lane + 32 * i) * 128u, sw, q);
-        __syncwarp();  // every lane is done reading this slot
-
-        // Refill the slot with the tile STAGES ahead.
-        if (lane == 0 && t + STAGES < t_end) {
-            const uint32_t bar = my_bars + 8 * stage;
-            mbar_expect_tx(bar, Cfg::kTileBytes);
-            tma_load_2d(tile, &tmap, 0, pb * N + pti * Cfg::kTileRows, bar, policy);
-            if (++pti == tpa) { pti = 0; ++pb; }
+            for (int i = 0; i < RPL; ++i) d2[i] = lds128(tile + static_cast<uint32_t>(lane + 32 * i) * 128u + (sw << 4)).x;
+        } else {
+#pragma unroll
+            for (int i = 0; i < RPL; ++i)
+                d2[i] = row_d2(tile + static_cast<uint32_t>(lane + 32 * i) * 128u, sw, q);
         }
+        __syncwarp();  // every lane is done reading this slot (and has read its descriptor)
+
+        if (lane == 0) produce(stage);   // refill the slot with this warp's tile STAGES ahead
+        __syncwarp();  // publishes the new descriptor
 
 #pragma unroll
         for (int i = 0; i < RPL; ++i) {
             const int slot = row0 + lane + 32 * i;
             const u64 key = slot < N ? make_key(d2[i], static_cast<uint32_t>(slot), largest) : 0ull;
+            if (p.debug & 1) top.lkey ^= key; else
             top.offer(key, lane, k);
         }
-
+        ++run_tiles;
         if (++stage == STAGES) { stage = 0; parity ^= 1u; }
-        if (++ti == tpa) { ti = 0; ++b; }
+        if (pend_actor >= 0) {   // the previous run's atomic has had a whole tile to come back
+            complete_pending(p, pend_actor, pend_key, pend_n, pend_ret, tag, lane);
+            pend_actor = -1;
+        }
     }
 
     const unsigned long long tl2 = p.timeline ? globaltimer_ns() : 0ull;
-    flush_actor(p, cur, gw, top, lane);
+    const int workers = n_warps < sc.n_chunks ? n_warps : sc.n_chunks;
+    if (cur >= 0 && !(p.debug & 4)) {
+        if (pend_actor >= 0) complete_pending(p, pend_actor, pend_key, pend_n, pend_ret, tag, lane);
+        if (flush_run(p, cur, run_tiles, tag, top, lane, pend_key, pend_n, pend_ret))
+            complete_pending(p, cur, pend_key, pend_n, pend_ret, tag, lane);
+        for (;;) {   // merge jobs: one actor each, first come first served
+            int job = 0;
+            if (lane == 0) job = static_cast<int>(atomicAdd(p.sched_ctr + 3, 1u));
+            job = __shfl_sync(kFull, job, 0);
+            if (job >= p.n_actors) break;
+            merge_job(p, job, tag, lane, p.timeline ? p.timeline + static_cast<int64_t>(gw) * 8 : nullptr);
+        }
+    }
+    else if (top.lkey == 0x1234567ull) p.topk_d2[0] = 0.f;   // keep the experiment's loads alive
+    if (lane == 0) {
+        // the last working warp re-arms the scheduler for the next launch (every other warp has
+        // consumed the result of its last counter atomic before it got here)
+        if (atomicAdd(p.sched_ctr + 1, 1u) == static_cast<unsigned>(workers) - 1u) {
+            p.sched_ctr[0] = 0u; p.sched_ctr[1] = 0u; p.sched_ctr[3] = 0u;
+            uint32_t next = tag + 1u;                      // next launch's epoch
+            if (next == 0u) {                              // wrapped: 0 is never a valid tag, and floors of the old
+                next = 1u;                                 // cycle would out-rank every new one in the atomicMax
+                for (int a = 0; a < p.n_actors; ++a) *actor_floor(p, a) = 0ull;
+            }
+            p.sched_ctr[2] = next;
+        }
+    }
     if (p.timeline && lane == 0) {
-        unsigned long long* o = p.timeline + gw * 4;
-        o[0] = tl0; o[1] = tl1; o[2] = tl2; o[3] = globaltimer_ns();
+        unsigned long long* o = p.timeline + static_cast<int64_t>(gw) * 8;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        o[0] = tl0; o[1] = tl1; o[2] = tl2; o[3] = globaltimer_ns(); o[4] = smid; o[5] = static_cast<unsigned long long>(run_tiles);
     }
 }
 

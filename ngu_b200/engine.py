@@ -252,7 +252,18 @@ class EpisodicEngine:
         check(self._lib.ngu_epi_scan_timing_end(self._h, C.byref(ms), C.byref(n)), self._h)
         return ms.value, n.value
 
+    def schedule_chunks(self):
+        """Test aid: the scan kernel's work schedule as a list of (first tile, end tile) per chunk."""
+        n = self.scan_geometry()["chunks"]
+        out = (C.c_int32 * 2)()
+        chunks = []
+        for i in range(n):
+            check(self._lib.ngu_epi_debug_chunk(self._h, i, out), self._h)
+            chunks.append((out[0], out[1]))
+        return chunks
+
     def scan_geometry(self) -> dict:
-        g = (C.c_int32 * 6)()
+        g = (C.c_int32 * 8)()
         check(self._lib.ngu_epi_scan_geometry(self._h, g), self._h)
-        return dict(grid=g[0], block=g[1], dyn_smem=g[2], tiles_per_warp=g[3], stages=g[4], tile_rows=g[5])
+        return dict(grid=g[0], block=g[1], dyn_smem=g[2], static_tiles_per_warp=g[3], stages=g[4], tile_rows=g[5],
+                    dynamic_chunk_tiles=g[6], chunks=g[7])

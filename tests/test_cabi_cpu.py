@@ -25,7 +25,7 @@ def test_exports_every_header_symbol(lib):
     assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.ngu_epi_abi_version() == 2
+    assert lib.ngu_epi_abi_version() == 3
 
 
 def test_struct_layout_matches_header():

@@ -42,11 +42,16 @@ def test_256x30k_properties_and_c_oracle_subset(cuda_device):
     assert torch.equal(eng._memory[:, 0], q)
     assert torch.equal(eng._memory[:, 1:], mem_before[:, 1:])
     assert eng.get_state()["cursor"] == 1
-    # oracle (plain C scan) on 8 whole actors
-    sub = [0, 3, 5, 100, 101, 200, 254, 255]
-    mem_sub = np.ascontiguousarray(memc[sub].transpose(1, 0, 2))
-    oi, od = c_oracle.scan_topk(mem_sub, q.cpu().numpy()[sub], k, True)
-    assert np.array_equal(oi.T, idx[sub]) and np.array_equal(od.T.view(np.uint32), d2[sub].view(np.uint32))
+    # oracle (plain C scan) on every actor, 32 at a time: actors of the statically scheduled part of the
+    # memory and of the dynamically scheduled part take different paths through the kernel
+    assert eng.scan_geometry()["dynamic_chunk_tiles"] > 0
+    qc = q.cpu().numpy()
+    for lo in range(0, B, 32):
+        sub = list(range(lo, lo + 32))
+        mem_sub = np.ascontiguousarray(memc[sub].transpose(1, 0, 2))
+        oi, od = c_oracle.scan_topk(mem_sub, qc[sub], k, True)
+        assert np.array_equal(oi.T, idx[sub]) and np.array_equal(od.T.view(np.uint32), d2[sub].view(np.uint32))
+    assert eng.get_state()["exchange_timeouts"] == 0
     # rewards: closed form from the engine's own top-k through the numpy oracle epilogue
     orc = EpisodicOracle(B, 16, k=k)
     want = orc.reward_from_topk(d2.T.copy(), None)

@@ -124,3 +124,75 @@ def test_create_errors(cuda_device):
         EpisodicEngine(4, 5, k=10, device=0)       # k > capacity: the reference's topk raises too
     with pytest.raises(NguEpiError):
         EpisodicEngine(4, 64, k=33, device=0)
+
+
+# ---- dynamic work schedule of the scan kernel (chunk counter, fence-free candidate publication,
+# ---- floors, incremental merge jobs) -------------------------------------------------------------
+def _check_partition(eng, B, N):
+    geo = eng.scan_geometry()
+    tpa = -(-N // geo["tile_rows"])
+    cover = np.zeros(B * tpa, np.int32)
+    chunks = eng.schedule_chunks()
+    assert len(chunks) == geo["chunks"]
+    for t, te in chunks:
+        assert 0 <= t <= te <= B * tpa
+        cover[t:te] += 1
+    assert (cover == 1).all(), "the schedule must hand out every tile exactly once"
+    return geo
+
+
+@pytest.mark.parametrize("B,N,sched", [(256, 30000, None), (37, 30000, None), (1, 30000, None), (64, 5000, None),
+                                        (300, 7777, "0.3,8,1"), (24, 12000, "0.5,2,1"), (24, 12000, "0.0,3,1")])
+def test_schedule_partitions_the_tile_space(cuda_device, monkeypatch, B, N, sched):
+    from ngu_b200.engine import EpisodicEngine
+    if sched:
+        monkeypatch.setenv("NGU_EPI_SCHED", sched)
+    eng = EpisodicEngine(B, N, device=0)
+    geo = _check_partition(eng, B, N)
+    if sched or (B, N) == (256, 30000):
+        assert geo["dynamic_chunk_tiles"] > 0, "expected the dynamic schedule for this shape"
+    eng.close()
+
+
+@pytest.mark.parametrize("sched,epoch", [("0.5,2,1", None), ("0.0,3,1", None), ("0.6,16,1", None),
+                                          ("0.5,2,1", "0xFFFFFFFD")])
+def test_dynamic_schedule_vs_oracle(cuda_device, monkeypatch, sched, epoch):
+    """Many short runs per actor (hundreds of flushes, floors, in-flight candidates, merge jobs) at a size
+    the oracle checks in full; `epoch` starts the launch epoch just below its 32-bit wrap."""
+    from ngu_b200.engine import EpisodicEngine
+    from oracle.episodic_oracle import EpisodicOracle
+    monkeypatch.setenv("NGU_EPI_SCHED", sched)
+    if epoch:
+        monkeypatch.setenv("NGU_EPI_DEBUG_EPOCH", epoch)
+    B, N, k = 24, 12000, 10
+    rng = np.random.default_rng(99)
+    mem0 = rng.standard_normal((N, B, 32), dtype=np.float32)
+    mem0[rng.random(N) < 0.2] = 0.0                       # ties among zero slots
+    mem0[:, 3, :] = 0.0                                   # an actor whose slots all tie
+    mem0[:, 4, 1:] = 0.0
+    mem0[:, 4, 0] = np.arange(N, dtype=np.float32) * 0.01  # ascending distances: every run publishes a full list
+    mem0[:, 5, 1:] = 0.0
+    mem0[:, 5, 0] = np.arange(N, dtype=np.float32)[::-1] * 0.01
+    orc = EpisodicOracle(B, N, k=k, use_c_scan=True)
+    orc.memory[...] = mem0
+    eng = EpisodicEngine(B, N, k=k, device=0)
+    assert eng.scan_geometry()["dynamic_chunk_tiles"] > 0
+    eng.load_memory(mem0)
+    for t in range(8):
+        q = rng.standard_normal((B, 32), dtype=np.float32)
+        q[4] = 0.0
+        q[5] = 0.0
+        alpha = (1.0 + 2.0 * rng.standard_normal(B)).astype(np.float32)
+        ref = orc.step(q, alpha)
+        r_int, _ = eng.step_host(q, alpha)
+        d2, idx = eng.topk()
+        assert np.array_equal(idx.T, ref["idx"]), f"step {t}: kNN slots differ"
+        assert np.array_equal(d2.T.view(np.uint32), ref["d2"].view(np.uint32)), f"step {t}: d^2 bits differ"
+        assert _rel(r_int.astype(np.float64), ref["reward"]).max() <= REL_TOL
+        done = rng.random(B) < 0.1
+        done[3:6] = False
+        orc.reset(done)
+        eng.reset_host(done)
+    assert eng.get_state()["exchange_timeouts"] == 0, "a merge gave up waiting for a candidate"
+    assert np.array_equal(eng.dump_memory(), orc.memory)
+    eng.close()
