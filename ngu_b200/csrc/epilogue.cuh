@@ -141,6 +141,8 @@ struct EpilogueParams {
     const float* rnd_targ;    // [B][128] RND target features
     float* alpha_out;         // [B] or null: the modulator computed by the RND phase
     P2PView p2p;              // used when phases & PH_EXCHANGE
+    unsigned int* host_flag;  // mapped host word or null: receives host_seq after the kernel's last write
+    unsigned int host_seq;
 };
 
 // Chan/Welford merge of (mean, var, count) with a batch (mpi_util.py:59-73), all f64.
@@ -224,9 +226,7 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
     // prefetching lines that the previous epilogue may still be writing is harmless.
     if (threadIdx.x < 5) prefetch_l2(reinterpret_cast<const char*>(st) + 128 * threadIdx.x);
     if (threadIdx.x == 5) prefetch_l2(p.plan);
-    if (finish && p.alpha)
-        for (int i = threadIdx.x * 32; i < B; i += THREADS * 32) prefetch_l2(p.alpha + i);
-    if (append)
+    if (append && !p.stage_q)
         for (int i = threadIdx.x; i < B; i += THREADS) prefetch_l2(p.q + static_cast<int64_t>(i) * 32);
 
     const bool rnd = finish && (p.phases & PH_RND) != 0;
@@ -254,16 +254,23 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
         }
     }
 
+    // The step's inputs (controllable states for the append, modulators) were complete before the scan
+    // kernel could start, so they are staged on chip NOW, while the scan streams.
+    if (finish && !rnd) {
+#pragma unroll 1
+        for (int i = threadIdx.x; i < B; i += THREADS) s_alpha[i] = p.alpha ? __ldcg(p.alpha + i) : 1.0f;
+    }
+    if (append && p.stage_q) {
+#pragma unroll 1
+        for (int i = threadIdx.x; i < B * 8; i += THREADS) s_q[i] = __ldcg(reinterpret_cast<const float4*>(p.q) + i);
+    }
+
     asm volatile("griddepcontrol.wait;" ::: "memory");               // scan kernel complete, its writes visible
 
     // ---- one batch of independent loads: everything the phases below need goes on chip ----
 #pragma unroll 1
     for (int i = threadIdx.x; i < B * k; i += THREADS) s_dist[i] = __ldcg(p.dist + i);
     if (finish) {
-        if (!rnd) {
-#pragma unroll 1
-            for (int i = threadIdx.x; i < B; i += THREADS) s_alpha[i] = p.alpha ? __ldcg(p.alpha + i) : 1.0f;
-        }
         if (p.sums_in && threadIdx.x < 2 * k + 1) s_sums[threadIdx.x] = __ldcg(p.sums_in + threadIdx.x);
         if (threadIdx.x < k) {
             s_mean[threadIdx.x] = __ldcg(&st->ed_mean[threadIdx.x]);
@@ -272,10 +279,6 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
         if (threadIdx.x >= 32 && threadIdx.x < 48) s_scal[threadIdx.x - 32] = __ldcg(&st->ed_count + (threadIdx.x - 32));
     }
     if (append) {
-        if (p.stage_q) {
-#pragma unroll 1
-            for (int i = threadIdx.x; i < B * 8; i += THREADS) s_q[i] = __ldcg(reinterpret_cast<const float4*>(p.q) + i);
-        }
         if (threadIdx.x == 64) s_cursor = __ldcg(&st->cursor);
     }
     if (threadIdx.x >= 96 && threadIdx.x < 96 + p.plan_len && threadIdx.x < 160) s_plan[threadIdx.x - 96] = __ldcg(p.plan + (threadIdx.x - 96));
@@ -465,6 +468,14 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
             *dst = p.stage_q ? s_q[i] : __ldcg(q4 + i);
         }
         if (threadIdx.x == 64) st->cursor = (cur + 1) % c.capacity;
+    }
+
+    if (p.host_flag) {   // ngu_epi_step_host: tell the spinning host that every write of the step has been issued
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned int*>(p.host_flag) = p.host_seq;
+        }
     }
 }
 

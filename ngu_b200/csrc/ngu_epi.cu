@@ -101,6 +101,7 @@ struct ngu_epi {
     double sched_static_frac = 0.6;          // share of the tiles handed out statically (experiments: NGU_EPI_SCHED=frac,c2)
     int sched_c2 = 16;                       // tiles per dynamic chunk
     int sched_min_avg = kDynMinAvgTilesDefault;   // fair share (tiles per warp) below which the schedule is static only
+    int sched_min_tiles = kMinTilesPerWarp;       // static-only schedules: at least this many tiles per warp
     int2* plan_dev = nullptr;        // pairwise-sum plan for n = B (epilogue rank sums)
     int plan_len = 0;
     // p2p rank-sum exchange (multi-GPU): local inbox + IPC-mapped peer inboxes
@@ -120,6 +121,14 @@ struct ngu_epi {
     float* pinned = nullptr;         // host: [B*32 q][B alpha] floats + B done bytes
     float* r_mapped = nullptr;       // host, mapped: [2][B] rewards written by the epilogue over PCIe (zero-copy)
     float* r_mapped_dev = nullptr;   // device alias of r_mapped
+    // completion of the *_host step: a mapped word the epilogue stores after its last write and the host
+    // spins on (a stream synchronize costs a few us more of driver wake-up per step).  Measured and
+    // rejected: reading the inputs in place from mapped memory instead of the staged H2D copy - 1 us
+    // better at 256 x 30k, 25 us worse on small shapes where the PCIe reads land on the critical path.
+    unsigned int* flag_mapped = nullptr;
+    unsigned int* flag_mapped_dev = nullptr;
+    unsigned int host_seq = 0;
+    bool host_flag_wait = true;      // experiments: NGU_EPI_HOST_PATH=sync -> stream synchronize instead
     // launch geometry
     Variant var{};
     CUtensorMap tmap{};
@@ -189,7 +198,7 @@ void plan_geometry(ngu_epi* h) {
     int min_chunk;
     if (T < h->sched_min_avg * max_warps || h->sched_static_frac >= 1.0 || h->sched_c2 <= 0) {
         int64_t tpw = (T + max_warps - 1) / max_warps;
-        if (tpw < kMinTilesPerWarp) tpw = kMinTilesPerWarp;
+        if (tpw < h->sched_min_tiles) tpw = h->sched_min_tiles;
         sc.s1 = static_cast<int32_t>(tpw);
         sc.n1 = static_cast<int32_t>((T + tpw - 1) / tpw);
         sc.n_chunks = sc.n1;
@@ -300,12 +309,13 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
     }
     if (const char* e = getenv("NGU_EPI_DEBUG_PHASES")) h->debug_phase_mask = atoi(e);
     if (const char* e = getenv("NGU_EPI_DEBUG_SCAN")) h->debug_scan = atoi(e);
-    if (const char* e = getenv("NGU_EPI_SCHED")) {   // experiments and tests: "static_frac,c2[,min_avg_tiles]"
-        double f = 0.6; int c2 = 16, mn = kDynMinAvgTilesDefault;
-        const int got = sscanf(e, "%lf,%d,%d", &f, &c2, &mn);
+    if (const char* e = getenv("NGU_EPI_SCHED")) {   // experiments and tests: "static_frac,c2[,min_avg_tiles[,min_tiles_per_warp]]"
+        double f = 0.6; int c2 = 16, mn = kDynMinAvgTilesDefault, mt = kMinTilesPerWarp;
+        const int got = sscanf(e, "%lf,%d,%d,%d", &f, &c2, &mn, &mt);
         if (got >= 1 && f >= 0.0) h->sched_static_frac = f;
         if (got >= 2) h->sched_c2 = c2;
         if (got >= 3 && mn >= 0) h->sched_min_avg = mn;
+        if (got >= 4 && mt >= 1) h->sched_min_tiles = mt;
     }
     plan_geometry(h);
 
@@ -353,6 +363,10 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
     CREATE_TRY(cudaMallocHost(&h->pinned, static_cast<size_t>(B) * 33 * sizeof(float) + B));
     CREATE_TRY(cudaHostAlloc(&h->r_mapped, static_cast<size_t>(B) * 2 * sizeof(float), cudaHostAllocMapped));
     CREATE_TRY(cudaHostGetDevicePointer(&h->r_mapped_dev, h->r_mapped, 0));
+    CREATE_TRY(cudaHostAlloc(&h->flag_mapped, 64, cudaHostAllocMapped));
+    CREATE_TRY(cudaHostGetDevicePointer(&h->flag_mapped_dev, h->flag_mapped, 0));
+    *h->flag_mapped = 0u;
+    if (const char* e = getenv("NGU_EPI_HOST_PATH")) h->host_flag_wait = std::strcmp(e, "sync") != 0;
 #undef CREATE_TRY
 
     EpiConsts& c = h->consts;
@@ -389,6 +403,7 @@ void ngu_epi_destroy(ngu_epi* h) {
     cudaFree(h->q_stage_dev); cudaFree(h->done_stage_dev);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->r_mapped) cudaFreeHost(h->r_mapped);
+    if (h->flag_mapped) cudaFreeHost(h->flag_mapped);
     delete h;
 }
 
@@ -422,7 +437,7 @@ static int launch_scan(ngu_epi* h, const float* q_dev, cudaStream_t s) {
     ScanParams sp{};
     sp.q = q_dev; sp.cand = h->cand;
     sp.n_actors = h->cfg.n_actors; sp.capacity = h->cfg.capacity; sp.k = h->cfg.k;
-    sp.largest = h->consts.largest; sp.sqrt_dist = h->consts.sqrt_dist;
+    sp.largest = h->consts.largest; sp.sqrt_dist = h->consts.sqrt_dist; sp.neg_zero2 = kNegZero2;
     sp.tiles_per_actor = h->tiles_per_actor;
     sp.max_cand = h->max_cand; sp.sched = h->sched; sp.sched_ctr = h->sched_ctr;
     sp.actor_state = h->actor_state;
@@ -440,11 +455,13 @@ static int launch_scan(ngu_epi* h, const float* q_dev, cudaStream_t s) {
 }
 
 struct RndArgs { const float* pred; const float* targ; float* alpha_out; };
+struct HostFlag { unsigned int* flag; unsigned int seq; };
 
 static int launch_epilogue(ngu_epi* h, int phases, const double* sums_in, const float* alpha, float* r_int,
                            float* r_epi, double* log_sums, const float* q, cudaStream_t s,
-                           const RndArgs* rnd = nullptr) {
+                           const RndArgs* rnd = nullptr, const HostFlag* hf = nullptr) {
     EpilogueParams ep{};
+    if (hf) { ep.host_flag = hf->flag; ep.host_seq = hf->seq; }
     if (rnd) { ep.rnd_pred = rnd->pred; ep.rnd_targ = rnd->targ; ep.alpha_out = rnd->alpha_out; }
     ep.dist = h->dist; ep.rank_sums = h->rank_sums; ep.sums_in = sums_in; ep.alpha = alpha;
     ep.r_int = r_int; ep.r_epi = r_epi; ep.log_sums = log_sums; ep.q = q; ep.memory = h->memory;
@@ -529,17 +546,21 @@ int ngu_epi_reset(ngu_epi* h, const uint8_t* done_dev, void* stream) {
     return NGU_OK;
 }
 
+static int step_impl(ngu_epi* h, const float* q_dev, const float* alpha_dev, float* r_int_dev, float* r_epi_dev,
+                     cudaStream_t s, const HostFlag* hf) {
+    int rc = launch_scan(h, q_dev, s);
+    if (rc) return rc;
+    // one epilogue launch: rank sums -> running-mean update -> rewards -> log-only stats -> append
+    return launch_epilogue(h, PH_RANKSUMS | PH_FINISH | PH_APPEND | PH_LOGFUSE, nullptr, alpha_dev, r_int_dev,
+                           r_epi_dev, nullptr, q_dev, s, nullptr, hf);
+}
+
 int ngu_epi_step(ngu_epi* h, const float* q_dev, const float* alpha_dev, float* r_int_dev, float* r_epi_dev,
                  void* stream) {
     if (!h || !q_dev || !r_int_dev) return fail(h, NGU_EINVAL, "null argument");
     int rc = bind_device(h);
     if (rc) return rc;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    rc = launch_scan(h, q_dev, s);
-    if (rc) return rc;
-    // one epilogue launch: rank sums -> running-mean update -> rewards -> log-only stats -> append
-    return launch_epilogue(h, PH_RANKSUMS | PH_FINISH | PH_APPEND | PH_LOGFUSE, nullptr, alpha_dev, r_int_dev,
-                           r_epi_dev, nullptr, q_dev, s);
+    return step_impl(h, q_dev, alpha_dev, r_int_dev, r_epi_dev, static_cast<cudaStream_t>(stream), nullptr);
 }
 
 int ngu_epi_step_rnd(ngu_epi* h, const float* q_dev, const float* pred_dev, const float* targ_dev, int32_t feat_dim,
@@ -556,6 +577,24 @@ int ngu_epi_step_rnd(ngu_epi* h, const float* q_dev, const float* pred_dev, cons
                            r_epi_dev, nullptr, q_dev, s, &ra);
 }
 
+// Spin on the mapped completion word the epilogue kernel stores after its last write (a stream
+// synchronize costs 5-10 us of driver wake-up per step); the stream is queried now and then so that a
+// failed launch cannot hang the caller.
+static int wait_host_flag(ngu_epi* h, unsigned int seq, cudaStream_t s) {
+    volatile unsigned int* f = h->flag_mapped;
+    for (unsigned spins = 1;; ++spins) {
+        if (*f == seq) return NGU_OK;
+        if ((spins & 0xFFFu) == 0u) {
+            const cudaError_t e = cudaStreamQuery(s);
+            if (e == cudaSuccess) return NGU_OK;          // completed: every write of the step is visible
+            if (e != cudaErrorNotReady) return fail(h, NGU_ECUDA, fmt("step failed: %s", cudaGetErrorString(e)));
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+}
+
 int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host, float* r_int_host,
                       float* r_epi_host) {
     if (!h || !q_host || !r_int_host) return fail(h, NGU_EINVAL, "null argument");
@@ -563,16 +602,24 @@ int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host, 
     if (rc) return rc;
     const size_t B = h->cfg.n_actors;
     cudaStream_t s = h->own_stream;
-    // one pinned H2D copy carries the step's controllable states and (optionally) the modulators;
-    // the rewards come back zero-copy: the epilogue kernel writes them straight into mapped host memory
+    const unsigned int seq = ++h->host_seq;
+    const HostFlag hf{h->flag_mapped_dev, seq};
+    // one pinned H2D copy carries the step's controllable states and (optionally) the modulators
     std::memcpy(h->pinned, q_host, B * 32 * sizeof(float));
     if (alpha_host) std::memcpy(h->pinned + B * 32, alpha_host, B * sizeof(float));
     CU_TRY(h, cudaMemcpyAsync(h->q_stage_dev, h->pinned, B * (alpha_host ? 33 : 32) * sizeof(float),
                               cudaMemcpyHostToDevice, s));
-    rc = ngu_epi_step(h, h->q_stage_dev, alpha_host ? h->a_stage_dev : nullptr, h->r_mapped_dev,
-                      h->r_mapped_dev + B, s);
+    const float* q_dev = h->q_stage_dev;
+    // the rewards come back zero-copy: the epilogue writes them straight into mapped host memory
+    rc = step_impl(h, q_dev, alpha_host ? q_dev + B * 32 : nullptr, h->r_mapped_dev, h->r_mapped_dev + B, s,
+                   h->host_flag_wait ? &hf : nullptr);
     if (rc) return rc;
-    CU_TRY(h, cudaStreamSynchronize(s));
+    if (h->host_flag_wait) {
+        rc = wait_host_flag(h, seq, s);
+        if (rc) return rc;
+    } else {
+        CU_TRY(h, cudaStreamSynchronize(s));
+    }
     std::memcpy(r_int_host, h->r_mapped, B * sizeof(float));
     if (r_epi_host) std::memcpy(r_epi_host, h->r_mapped + B, B * sizeof(float));
     return NGU_OK;

@@ -97,6 +97,7 @@ struct ScanParams {
     int32_t tiles_per_actor; // ceil(N / TILE_ROWS)
     int32_t max_cand;        // candidate entries reserved per actor (worst case: every run publishes k)
     int32_t sqrt_dist;       // 1: dist = sqrt(d2) (reference), 0: dist = d2 (paper)
+    unsigned long long neg_zero2;   // (-0.0f, -0.0f): opaque addend of the packed squares, see f2_sq
     ScanSched sched;
     unsigned int* sched_ctr;       // [0] dynamic chunk counter, [1] finished warps, [3] merge-job counter (zero between
                                    // launches), [2] launch epoch = tag of this launch's candidates and floors (never 0)
@@ -166,10 +167,15 @@ __device__ __forceinline__ void st_ll(u64* dst, u64 key, uint32_t tag) {
     const u64 w1 = (key << 32) | tag;
     asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
 }
-__device__ __forceinline__ bool ld_ll(const u64* src, uint32_t tag, u64& key) {
-    u64 w0, w1;
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
-    key = (w0 & 0xFFFFFFFF00000000ull) | (w1 >> 32);
+// raw tagged words of one candidate; the tag check is left to the caller so that a batch of these loads
+// can be issued back to back (a check right behind each load makes the warp wait out every round trip)
+__device__ __forceinline__ void ld_ll_raw(const u64* src, u64& w0, u64& w1) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+}
+__device__ __forceinline__ void lds_2x64(uint32_t addr, u64& a, u64& b) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ bool ll_ready(u64 w0, u64 w1, uint32_t tag) {
     return static_cast<uint32_t>(w0) == tag && static_cast<uint32_t>(w1) == tag;
 }
 __device__ __forceinline__ u64 ld_volatile_u64(const u64* src) {
@@ -178,17 +184,6 @@ __device__ __forceinline__ u64 ld_volatile_u64(const u64* src) {
     return v;
 }
 constexpr int kLLSpinLimit = 1 << 22;   // ~ seconds; a healthy wait is about one tile time
-__device__ __forceinline__ u64 wait_ll(unsigned long long* timeouts, const u64* src, uint32_t tag) {
-    u64 key;
-    int spins = 0;
-    while (!ld_ll(src, tag, key)) {
-        if (++spins > kLLSpinLimit) {
-            atomicAdd(timeouts, 1ull);
-            return 0ull;
-        }
-    }
-    return key;
-}
 // floor word -> the largest key that is certainly NOT needed (0 = no floor)
 __device__ __forceinline__ u64 floor_key(u64 floor_word, uint32_t tag) {
     const uint32_t hi = static_cast<uint32_t>(floor_word);
@@ -228,55 +223,152 @@ __device__ __forceinline__ void complete_pending(const ScanParams& p, int actor,
     if (lane < pend_n) st_ll(cand + (pos + lane) * 2, pend_key, tag);
 }
 
-// When a warp has streamed its last tile it takes merge jobs (one actor each) from a global counter
-// until none are left.  Warps finish up to ~20 us apart, so the jobs are picked up by the early
-// finishers while the rest still stream, and a job is worked INCREMENTALLY: the warp consumes the
+// Offer the candidates [from, to) of one actor to m.  They are staged through the warp's (now idle) tile
+// buffers with 16-byte cp.async copies, sixteen batches of 32 in flight, and consumed from shared memory
+// in a ROLLED loop.  Three simpler forms all cost ~0.45 us per batch (40 us for the 2 350 candidates of a
+// B = 1 scan): a tag check right behind each load waits out every round trip; unrolled batches each run
+// their own cold copy of the insert / bitonic code; a register ring cannot be rotated without reading
+// registers whose loads are still in flight.
+__device__ __forceinline__ void stage_candidates(const u64* cand, int from, int to, int lane, uint32_t stage) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        const int i = from + 32 * u + lane;
+        if (i < to)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage + (32 * u + lane) * 16), "l"(cand + i * 2)
+                         : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+// staged entry e (global index base + e) -> key; polls global memory while its tags are not the epoch's
+__device__ __forceinline__ u64 staged_key(const ScanParams& p, const u64* cand, int base, int e, uint32_t tag, uint32_t stage) {
+    u64 w0, w1;
+    lds_2x64(stage + e * 16, w0, w1);
+    int polls = 0;
+    while (!ll_ready(w0, w1, tag)) {                      // not yet published: poll it
+        ld_ll_raw(cand + (base + e) * 2, w0, w1);
+        if (++polls > kLLSpinLimit) { atomicAdd(p.timeouts, 1ull); return 0ull; }
+    }
+    return (w0 & 0xFFFFFFFF00000000ull) | (w1 >> 32);
+}
+__device__ __forceinline__ void consume_candidates(const ScanParams& p, const u64* cand, int from, int to, uint32_t tag, int lane,
+                                                   uint32_t stage /* 8 KB smem */, WarpTopK& m) {
+    const int k = p.k;
+    for (int done = from; done < to; done += 512) {
+        const int end = to - done < 512 ? to : done + 512;
+        stage_candidates(cand, done, end, lane, stage);
+#pragma unroll 1
+        for (int e0 = 0; e0 < end - done; e0 += 32) {
+            const int e = e0 + lane;
+            m.offer(e < end - done ? staged_key(p, cand, done, e, tag, stage) : 0ull, lane, k);
+        }
+    }
+}
+// The same for `nlists` complete, sorted lists of k keys each (static schedules), offered RANK-MAJOR: the
+// best key of every list first, then the second best, ...  The threshold is near its final value after
+// the first rank, and as soon as a whole rank fails it the deeper (smaller) ranks cannot pass either: a
+// merge touches 2-3 ranks and does ~15 insertions, where storage order does ~10 ln(rows / 10) of them
+// (~200 cycles each, one warp) plus a threshold pass.
+__device__ __forceinline__ void consume_lists(const ScanParams& p, const u64* cand, int nlists, uint32_t tag, int lane,
+                                              uint32_t stage /* 8 KB smem */, WarpTopK& m) {
+    const int k = p.k;
+    const int per_round = 512 / k;                        // whole lists per staging round
+    for (int l0 = 0; l0 < nlists; l0 += per_round) {
+        const int nl = nlists - l0 < per_round ? nlists - l0 : per_round;
+        stage_candidates(cand, l0 * k, (l0 + nl) * k, lane, stage);
+#pragma unroll 1
+        for (int r = 0; r < k; ++r) {
+            unsigned passed = 0;
+#pragma unroll 1
+            for (int lb = 0; lb < nl; lb += 32) {
+                const int l = lb + lane;
+                const u64 key = l < nl ? staged_key(p, cand, l0 * k, l * k + r, tag, stage) : 0ull;
+                passed |= __ballot_sync(kFull, key > m.thr);
+                m.offer(key, lane, k);
+            }
+            if (!passed) break;
+        }
+    }
+}
+
+// DYNAMIC schedules.  When a warp has streamed its last tile it takes merge jobs (one actor each) from a
+// global counter until none are left.  Warps finish up to ~20 us apart, so the jobs are picked up by the
+// early finishers while the rest still stream, and a job is worked INCREMENTALLY: the warp consumes the
 // actor's candidates as they are published (the low half of the actor's counter says how many are
 // reserved, the tags say which have landed) and keeps the running top-k in registers; when the tile
 // count finally completes, only the last few candidates are left to read - one round trip after the
 // last tile instead of a whole merge.  Nothing is merged inside the streaming loop, so the loop
 // carries no merge registers.
-__device__ __forceinline__ void merge_job(const ScanParams& p, int actor, uint32_t tag, int lane,
+__device__ __forceinline__ void merge_job(const ScanParams& p, int actor, uint32_t tag, int lane, uint32_t stage /* 8 KB smem */,
                                           unsigned long long* tl /* debug timeline record or null */) {
     const int k = p.k;
     u64* ctr = actor_ctr(p, actor);
     const u64* cand = p.cand + static_cast<int64_t>(actor) * p.max_cand * 2;
     WarpTopK m;
-    // any floor published during this launch is a valid lower bound of the final k-th best
-    m.reset(floor_key(ld_volatile_u64(actor_floor(p, actor)), tag));
+    m.reset();
     int done = 0, spins = 0;
     uint32_t n = 0;
+    const unsigned long long dbg_t0 = tl ? globaltimer_ns() : 0ull;
     for (;;) {
+        // Any floor published during this launch is a valid lower bound of the final k-th best, and it
+        // keeps rising while the runs flush: re-read it every round.
+        const u64 fw = ld_volatile_u64(actor_floor(p, actor));
         const u64 c = ld_volatile_u64(ctr);
         const bool complete = static_cast<uint32_t>(c >> 32) == static_cast<uint32_t>(p.tiles_per_actor);
         n = static_cast<uint32_t>(c);
         if (n == kWrittenDirectly) break;                 // (only ever set together with the full tile count)
+        m.floor = umax64(m.floor, floor_key(fw, tag));
+        m.thr = umax64(m.thr, m.floor);
         const int avail = static_cast<int>(n);
-        while (done < avail) {                            // eight independent loads in flight per lane
-            u64 key[8];
-            unsigned okm = 0;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = done + 32 * u + lane;
-                key[u] = 0ull;
-                if (i >= avail || ld_ll(cand + i * 2, tag, key[u])) okm |= 1u << u;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (!((okm >> u) & 1u)) key[u] = wait_ll(p.timeouts, cand + (done + 32 * u + lane) * 2, tag);
-                m.offer(key[u], lane, k);
-            }
-            done += 256;
-        }
+        consume_candidates(p, cand, done, avail, tag, lane, stage, m);
         done = avail;
         if (complete) break;
         if (++spins > kLLSpinLimit) { if (lane == 0) atomicAdd(p.timeouts, 1ull); break; }
     }
     __syncwarp();
     if (lane == 0) *ctr = 0ull;                           // re-arm for the next launch: every arrival has been performed
-    if (tl && lane == 0) { tl[6] = n; tl[7] = globaltimer_ns(); }
+    if (tl && lane == 0) { tl[5] = dbg_t0; tl[6] = n; tl[7] = globaltimer_ns(); }   // merge job: start, candidates, end
     if (n == kWrittenDirectly || (p.debug & 8)) return;
     write_knn(knn_out(p, actor), k, knn_flags(p), m.lkey, lane);
+}
+
+// STATIC schedules (small shapes: every warp owns exactly one chunk of s1 tiles).  These are bound by
+// latency, not bandwidth, so the protocol is the shortest one: a run's slot in the actor's candidate buffer
+// follows from the chunk it belongs to, so its k keys are published at once (no reservation round trip);
+// arrivals are counted in tiles; the run whose arrival completes the actor merges it - when the warp has
+// finished streaming, so again nothing is merged inside the loop - and knows exactly when, no polling.
+__device__ __forceinline__ bool flush_run_static(const ScanParams& p, int actor, int run_tiles, int run_first_ti, uint32_t tag,
+                                                 const WarpTopK& top, int lane, u64& ret) {
+    const int k = p.k;
+    const int tpa = p.tiles_per_actor;
+    if (run_tiles == tpa) {                         // this warp scanned the whole actor
+        write_knn(knn_out(p, actor), k, knn_flags(p), top.lkey, lane);
+        return false;
+    }
+    const int s1 = p.sched.s1, t0 = actor * tpa;
+    const int slot = (t0 + run_first_ti) / s1 - t0 / s1;     // chunks of the actor before this run's chunk
+    u64* cand = p.cand + static_cast<int64_t>(actor) * p.max_cand * 2;
+    if (lane < k) st_ll(cand + (slot * k + lane) * 2, top.lkey, tag);
+    if (lane == 0) ret = atomicAdd(actor_ctr(p, actor), static_cast<u64>(run_tiles) << 32);
+    return true;
+}
+__device__ __forceinline__ void finish_static(const ScanParams& p, int actor, int run_tiles, u64 ret, uint32_t tag, int lane,
+                                              uint32_t stage, unsigned long long* tl) {
+    const u64 prev = __shfl_sync(kFull, ret, 0);
+    const int tpa = p.tiles_per_actor;
+    if (static_cast<uint32_t>(prev >> 32) + static_cast<uint32_t>(run_tiles) != static_cast<uint32_t>(tpa)) return;
+    // this run completed the actor; the other runs' keys are published or on their way (their tags are polled)
+    if (lane == 0) *actor_ctr(p, actor) = 0ull;    // re-arm for the next launch
+    if (p.debug & 8) return;
+    const int k = p.k, s1 = p.sched.s1, t0 = actor * tpa;
+    const int nparts = (t0 + tpa - 1) / s1 - t0 / s1 + 1;
+    const u64* cand = p.cand + static_cast<int64_t>(actor) * p.max_cand * 2;
+    WarpTopK m;
+    m.reset();
+    const unsigned long long dbg_t0 = tl ? globaltimer_ns() : 0ull;
+    consume_lists(p, cand, nparts, tag, lane, stage, m);
+    write_knn(knn_out(p, actor), k, knn_flags(p), m.lkey, lane);
+    if (tl && lane == 0) { tl[5] = dbg_t0; tl[6] = static_cast<unsigned long long>(nparts * k); tl[7] = globaltimer_ns(); }
 }
 
 // ---- PTX wrappers ---------------------------------------------------------
@@ -333,35 +425,50 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     return v;
 }
 
-__device__ __forceinline__ float sqdiff(float m, float q) {
-    const float d = __fsub_rn(m, q);
-    return __fmul_rn(d, d);
-}
+// ---- packed fp32 arithmetic (sm_100: FADD2 / FFMA2 work on two fp32 values in a 64-bit register pair,
+// each half IEEE round-to-nearest) -----------------------------------------------------------------
+// The distance of one row is 32 subtractions, 32 squares and 31 additions in a FIXED order with every
+// result rounded separately (that is what makes d^2 bit-identical to torch-CPU); done as scalar FADD /
+// FMUL they are 95 of the ~270 instructions a warp issues per tile, and the warps are busy enough on
+// that path for it to show in the kernel time.  Packed, they are 16 + 16 + 12 (+ 7 scalar adds).
+// The square is written fma(d, d, z) with z = (-0.0, -0.0) passed as a KERNEL PARAMETER:
+//   * ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (single rounding -> different bits) even
+//     with --fmad=false, and it folds a literal -0.0 addend back into a multiply first;
+//   * an addend it cannot see through keeps the product a separately rounded FFMA2 result, and
+//     x*x + (-0.0) == x*x for every x (a square is never -0.0), so the bits are those of mul.rn.
+using f2 = unsigned long long;
+constexpr f2 kNegZero2 = 0x8000000080000000ull;
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 f2_sq(f2 d, f2 z) { f2 r; asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(d), "l"(z)); return r; }
+__device__ __forceinline__ void f2_unpack(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 
-// d^2 of one swizzled 128-byte row against the register-resident query.
-// row_addr = shared address of the row start, sw = row & 7.
-__device__ __forceinline__ float row_d2(uint32_t row_addr, uint32_t sw, const float (&q)[32]) {
-    float a[8];
+// d^2 of one swizzled 128-byte row against the register-resident query (16 packed pairs).
+// row_addr = shared address of the row start, sw = row & 7, z = kNegZero2 from the parameters.
+__device__ __forceinline__ float row_d2(uint32_t row_addr, uint32_t sw, const f2 (&q)[16], f2 z) {
+    f2 a[4];   // lane accumulators (a0,a1) (a2,a3) (a4,a5) (a6,a7)
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        const float4 m = lds128(row_addr + ((static_cast<uint32_t>(c) ^ sw) << 4));
-        const int l0 = 4 * (c & 1);
-        const float s0 = sqdiff(m.x, q[4 * c + 0]);
-        const float s1 = sqdiff(m.y, q[4 * c + 1]);
-        const float s2 = sqdiff(m.z, q[4 * c + 2]);
-        const float s3 = sqdiff(m.w, q[4 * c + 3]);
+        f2 m01, m23;
+        lds_2x64(row_addr + ((static_cast<uint32_t>(c) ^ sw) << 4), m01, m23);
+        const f2 s01 = f2_sq(f2_sub(m01, q[2 * c]), z);
+        const f2 s23 = f2_sq(f2_sub(m23, q[2 * c + 1]), z);
+        const int i = 2 * (c & 1);   // elements 4c..4c+3 feed lane accumulators 4(c&1)..4(c&1)+3
         if (c < 2) {  // first contribution to each lane accumulator: 0 + s == s
-            a[l0 + 0] = s0; a[l0 + 1] = s1; a[l0 + 2] = s2; a[l0 + 3] = s3;
+            a[i] = s01; a[i + 1] = s23;
         } else {
-            a[l0 + 0] = __fadd_rn(a[l0 + 0], s0);
-            a[l0 + 1] = __fadd_rn(a[l0 + 1], s1);
-            a[l0 + 2] = __fadd_rn(a[l0 + 2], s2);
-            a[l0 + 3] = __fadd_rn(a[l0 + 3], s3);
+            a[i] = f2_add(a[i], s01);
+            a[i + 1] = f2_add(a[i + 1], s23);
         }
     }
-    float h = a[0];
+    float lo, hi;
+    f2_unpack(a[0], lo, hi);
+    float h = __fadd_rn(lo, hi);
 #pragma unroll
-    for (int l = 1; l < 8; ++l) h = __fadd_rn(h, a[l]);
+    for (int i = 1; i < 4; ++i) {
+        f2_unpack(a[i], lo, hi);
+        h = __fadd_rn(__fadd_rn(h, lo), hi);
+    }
     return h;
 }
 
@@ -469,13 +576,17 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
     const bool largest = p.largest != 0;
     const int k = p.k;
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
-    float q[32];
+    f2 q[16];
     WarpTopK top;
     int cur = -1;        // actor whose list is being built
     int run_tiles = 0;   // tiles of `cur` in the list
     bool run_start = false;     // the tile being consumed is the first of a run
     int pend_actor = -1, pend_n = 0;   // flushed run whose reserve/arrive atomic has not been read yet
     u64 pend_key = 0ull, pend_ret = 0ull;
+    // static schedules: the warp's chunk can begin inside one actor and end inside another; the first of
+    // these two partial runs waits here until the warp has finished streaming (pend_n = its tile count)
+    const bool static_sched = sc.n_chunks == sc.n1;
+    int run_first = 0;                 // tile-in-actor of the current run's first tile
     int stage = 0;
     uint32_t parity = 0;
     bool first = true;
@@ -486,11 +597,19 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
         if (b < 0) break;
         if (b != cur) {
             if (cur >= 0 && !(p.debug & 4)) {
-                if (pend_actor >= 0) complete_pending(p, pend_actor, pend_key, pend_n, pend_ret, tag, lane);
-                pend_actor = flush_run(p, cur, run_tiles, tag, top, lane, pend_key, pend_n, pend_ret) ? cur : -1;
+                if (static_sched) {
+                    if (pend_actor >= 0)   // (cannot happen: only a chunk's first and last run are partial)
+                        finish_static(p, pend_actor, pend_n, pend_ret, tag, lane, my_tiles, nullptr);
+                    pend_actor = flush_run_static(p, cur, run_tiles, run_first, tag, top, lane, pend_ret) ? cur : -1;
+                    pend_n = run_tiles;
+                } else {
+                    if (pend_actor >= 0) complete_pending(p, pend_actor, pend_key, pend_n, pend_ret, tag, lane);
+                    pend_actor = flush_run(p, cur, run_tiles, tag, top, lane, pend_key, pend_n, pend_ret) ? cur : -1;
+                }
             }
             cur = b;
             run_tiles = 0;
+            run_first = ti;
             run_start = true;
         }
 
@@ -499,10 +618,7 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
         if (run_start) {   // query row and floor arrived with the tile (same mbarrier)
             const uint32_t aux = my_aux + stage * Cfg::kAuxBytes;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 v = lds128(aux + 16 * c);
-                q[4 * c + 0] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w;
-            }
+            for (int c = 0; c < 8; ++c) lds_2x64(aux + 16 * c, q[2 * c], q[2 * c + 1]);
             u64 fw;
             asm volatile("ld.shared.u64 %0, [%1];" : "=l"(fw) : "r"(aux + 128) : "memory");
             // keys at or below the actor's published floor cannot make the final top-k
@@ -518,7 +634,7 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
         } else {
 #pragma unroll
             for (int i = 0; i < RPL; ++i)
-                d2[i] = row_d2(tile + static_cast<uint32_t>(lane + 32 * i) * 128u, sw, q);
+                d2[i] = row_d2(tile + static_cast<uint32_t>(lane + 32 * i) * 128u, sw, q, p.neg_zero2);
         }
         __syncwarp();  // every lane is done reading this slot (and has read its descriptor)
 
@@ -534,7 +650,7 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
         }
         ++run_tiles;
         if (++stage == STAGES) { stage = 0; parity ^= 1u; }
-        if (pend_actor >= 0) {   // the previous run's atomic has had a whole tile to come back
+        if (pend_actor >= 0 && !static_sched) {   // the previous run's atomic has had a whole tile to come back
             complete_pending(p, pend_actor, pend_key, pend_n, pend_ret, tag, lane);
             pend_actor = -1;
         }
@@ -542,7 +658,13 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
 
     const unsigned long long tl2 = p.timeline ? globaltimer_ns() : 0ull;
     const int workers = n_warps < sc.n_chunks ? n_warps : sc.n_chunks;
-    if (cur >= 0 && !(p.debug & 4)) {
+    unsigned long long* tl_rec = p.timeline ? p.timeline + static_cast<int64_t>(gw) * 8 : nullptr;
+    if (cur >= 0 && !(p.debug & 4) && static_sched) {
+        u64 ret = 0ull;
+        const bool last_partial = flush_run_static(p, cur, run_tiles, run_first, tag, top, lane, ret);
+        if (pend_actor >= 0) finish_static(p, pend_actor, pend_n, pend_ret, tag, lane, my_tiles, tl_rec);
+        if (last_partial) finish_static(p, cur, run_tiles, ret, tag, lane, my_tiles, tl_rec);
+    } else if (cur >= 0 && !(p.debug & 4)) {
         if (pend_actor >= 0) complete_pending(p, pend_actor, pend_key, pend_n, pend_ret, tag, lane);
         if (flush_run(p, cur, run_tiles, tag, top, lane, pend_key, pend_n, pend_ret))
             complete_pending(p, cur, pend_key, pend_n, pend_ret, tag, lane);
@@ -551,7 +673,7 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
             if (lane == 0) job = static_cast<int>(atomicAdd(p.sched_ctr + 3, 1u));
             job = __shfl_sync(kFull, job, 0);
             if (job >= p.n_actors) break;
-            merge_job(p, job, tag, lane, p.timeline ? p.timeline + static_cast<int64_t>(gw) * 8 : nullptr);
+            merge_job(p, job, tag, lane, my_tiles, tl_rec);
         }
     }
     else if (top.lkey == 0x1234567ull) p.topk_d2[0] = 0.f;   // keep the experiment's loads alive
@@ -572,7 +694,7 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
         unsigned long long* o = p.timeline + static_cast<int64_t>(gw) * 8;
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        o[0] = tl0; o[1] = tl1; o[2] = tl2; o[3] = globaltimer_ns(); o[4] = smid; o[5] = static_cast<unsigned long long>(run_tiles);
+        o[0] = tl0; o[1] = tl1; o[2] = tl2; o[3] = globaltimer_ns(); o[4] = smid;
     }
 }
 

@@ -6,7 +6,7 @@ import numpy as np, torch
 from ngu_b200.engine import EpisodicEngine
 
 pct = lambda x: [round(float(v), 2) for v in np.percentile(x, [0, 10, 50, 90, 100])]
-CASES = [(256, 30000, 0, 0, "0.6,8"), (256, 30000, 0, 0, "0.6,16"), (256, 30000, 0, 0, "0.4,16"), (256, 30000, 0, 0, "1.0,0"), (1024, 30000, 0, 0, "0.6,16")]
+CASES = [(64, 5000, 0, d, "0.6,16") for d in (0, 8, 4, 5, 7)]
 for B, N, variant, dbg, sched in CASES:
     os.environ["NGU_EPI_DEBUG_SCAN"] = str(dbg)
     os.environ["NGU_EPI_SCHED"] = sched
@@ -40,14 +40,6 @@ for B, N, variant, dbg, sched in CASES:
     tiles = t[:, 5]
     sm_tiles = np.array([tiles[smid == s].sum() for s in np.unique(smid)])
     out["last_run_tiles"] = pct(tiles)
-    mg = t[:, 7] > 0
-    if mg.any():
-        t_done = (t[mg, 7] - t0) / 1e3
-        out["merge_warps"] = int(mg.sum())
-        out["cand_per_actor"] = pct(t[mg, 6][t[mg, 6] < 2**31])
-        out["actor_complete_seen_us"] = pct(t_done)
-        out["wait_for_complete_us"] = pct(t_done - rel[mg, 2])
-        out["merge_after_complete_us"] = pct(rel[mg, 3] - t_done)
     print(json.dumps(out), flush=True)
     if dbg == 0 and sched == "1.0,0":
         np.save("gpurun_out/timeline_b256.npy", np.concatenate([rel, smid[:, None]], axis=1))

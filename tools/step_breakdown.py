@@ -28,7 +28,7 @@ def run(B, N, pdl, phases, variant=0, steps=200, warm=30):
 
 
 if __name__ == "__main__":
-    for (B, N) in [(256, 30000), (1024, 30000), (64, 5000), (32, 30000), (1, 30000)]:
-        for variant in (0, 4):
+    for (B, N) in [(64, 5000), (32, 30000), (1, 30000), (8, 30000), (256, 1000)]:
+        for variant in (0,):
             for pdl, phases in [(1, 15), (1, 0)]:
                 print(json.dumps(run(B, N, pdl, phases, variant)), flush=True)
