@@ -150,3 +150,39 @@ def test_cuda_graph_replay_equals_eager(cuda_device):
     assert a.epi_novel.memory_idx == b.epi_novel.memory_idx == 8
     np.testing.assert_allclose(a.epi_novel.ed_rms.mean, b.epi_novel.ed_rms.mean, rtol=1e-5)
     np.testing.assert_allclose(a.ll_novel.ll_rms.mean, b.ll_novel.ll_rms.mean, rtol=1e-5)
+
+
+def test_collect_sequence_style_loop_300_steps(cuda_device):
+    """BASELINE configs[3] shape in miniature: the drop-in inside a collect_sequence-style
+    loop (ngu_agent.py:56-94: reward query -> reset of finished actors) for one 300-step sequence with
+    random episode ends, the ring wrapping several times and the RND modulator clipped at both ends
+    (L = 5), against the oracle step by step."""
+    import ngu_b200.pytorch_util as ptu
+    from ngu_b200.engine import DEFAULT_HYPR
+    from ngu_b200.intrinsic_novelty import IntrinsicNovelty
+    from oracle.episodic_oracle import EpisodicOracle
+    ptu.init_device()
+    B, N, k, steps = 32, 96, 10, 300
+    hy = dict(DEFAULT_HYPR, episodic_memory_capacity=N)
+    inn = IntrinsicNovelty(B, 18, (1, 84, 84), hy, _NullLogger()).to(ptu.device)
+    inn.epi_novel.embedding = lambda x: x
+    orc = EpisodicOracle(B, N, k=k)
+    rng = np.random.default_rng(4)
+    n_resets = 0
+    for t in range(steps):
+        q = rng.standard_normal((B, 32), dtype=np.float32)
+        alpha = (1.0 + 3.0 * rng.standard_normal(B)).astype(np.float32)     # well below 1 and above 5
+        inn.ll_novel.compute_lifelong_curiosity = lambda obs, a=alpha: torch.from_numpy(a.copy())
+        out = inn.compute_intrinsic_novelty(torch.from_numpy(q))
+        want = orc.step(q, alpha)
+        rel = np.abs(out.numpy()[:, 0].astype(np.float64) - want["reward"]) / np.maximum(np.abs(want["reward"]), 1e-30)
+        assert rel.max() <= 1e-5, f"step {t}: {rel.max():.2e}"
+        _, idx = inn.epi_novel.knn()
+        assert np.array_equal(idx.T, want["idx"]), f"step {t}: kNN slots differ"
+        done = rng.random(B) < 0.02
+        n_resets += int(done.sum())
+        orc.reset(done)
+        inn.reset_memory_if_done(torch.from_numpy(done))
+    assert n_resets > 100 and inn.epi_novel.memory_idx == steps % N
+    assert np.array_equal(inn.epi_novel.episodic_memory.cpu().numpy(), orc.memory)
+    assert inn.epi_novel.ed_rms.count == k + steps * B
