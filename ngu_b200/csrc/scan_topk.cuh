@@ -220,6 +220,10 @@ __device__ __forceinline__ void complete_pending(const ScanParams& p, int actor,
                                                  uint32_t tag, int lane) {
     const unsigned pos = static_cast<unsigned>(__shfl_sync(kFull, pend_ret, 0));
     u64* cand = p.cand + static_cast<int64_t>(actor) * p.max_cand * 2;
+    if (pos + static_cast<unsigned>(pend_n) > static_cast<unsigned>(p.max_cand)) {   // cannot happen (max_cand is the
+        if (lane == 0) atomicAdd(p.timeouts, 1ull);                                   // worst case); never write out of bounds
+        return;
+    }
     if (lane < pend_n) st_ll(cand + (pos + lane) * 2, pend_key, tag);
 }
 
@@ -348,6 +352,10 @@ __device__ __forceinline__ bool flush_run_static(const ScanParams& p, int actor,
     const int s1 = p.sched.s1, t0 = actor * tpa;
     const int slot = (t0 + run_first_ti) / s1 - t0 / s1;     // chunks of the actor before this run's chunk
     u64* cand = p.cand + static_cast<int64_t>(actor) * p.max_cand * 2;
+    if ((slot + 1) * k > p.max_cand) {                       // cannot happen; never write out of bounds
+        if (lane == 0) atomicAdd(p.timeouts, 1ull);
+        return false;
+    }
     if (lane < k) st_ll(cand + (slot * k + lane) * 2, top.lkey, tag);
     if (lane == 0) ret = atomicAdd(actor_ctr(p, actor), static_cast<u64>(run_tiles) << 32);
     return true;

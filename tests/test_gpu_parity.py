@@ -154,9 +154,11 @@ def test_schedule_partitions_the_tile_space(cuda_device, monkeypatch, B, N, sche
     eng.close()
 
 
-@pytest.mark.parametrize("sched,epoch", [("0.5,2,1", None), ("0.0,3,1", None), ("0.6,16,1", None),
-                                          ("0.5,2,1", "0xFFFFFFFD")])
-def test_dynamic_schedule_vs_oracle(cuda_device, monkeypatch, sched, epoch):
+@pytest.mark.parametrize("sched,epoch,k,mode", [("0.5,2,1", None, 10, "reference"), ("0.0,3,1", None, 10, "reference"),
+                                                 ("0.6,16,1", None, 10, "reference"), ("0.5,2,1", "0xFFFFFFFD", 10, "reference"),
+                                                 ("0.5,2,1", None, 32, "reference"), ("0.3,4,1", None, 1, "reference"),
+                                                 ("0.5,2,1", None, 10, "paper")])
+def test_dynamic_schedule_vs_oracle(cuda_device, monkeypatch, sched, epoch, k, mode):
     """Many short runs per actor (hundreds of flushes, floors, in-flight candidates, merge jobs) at a size
     the oracle checks in full; `epoch` starts the launch epoch just below its 32-bit wrap."""
     from ngu_b200.engine import EpisodicEngine
@@ -164,7 +166,7 @@ def test_dynamic_schedule_vs_oracle(cuda_device, monkeypatch, sched, epoch):
     monkeypatch.setenv("NGU_EPI_SCHED", sched)
     if epoch:
         monkeypatch.setenv("NGU_EPI_DEBUG_EPOCH", epoch)
-    B, N, k = 24, 12000, 10
+    B, N = 24, 12000
     rng = np.random.default_rng(99)
     mem0 = rng.standard_normal((N, B, 32), dtype=np.float32)
     mem0[rng.random(N) < 0.2] = 0.0                       # ties among zero slots
@@ -173,9 +175,9 @@ def test_dynamic_schedule_vs_oracle(cuda_device, monkeypatch, sched, epoch):
     mem0[:, 4, 0] = np.arange(N, dtype=np.float32) * 0.01  # ascending distances: every run publishes a full list
     mem0[:, 5, 1:] = 0.0
     mem0[:, 5, 0] = np.arange(N, dtype=np.float32)[::-1] * 0.01
-    orc = EpisodicOracle(B, N, k=k, use_c_scan=True)
+    orc = EpisodicOracle(B, N, k=k, mode=mode, use_c_scan=True)
     orc.memory[...] = mem0
-    eng = EpisodicEngine(B, N, k=k, device=0)
+    eng = EpisodicEngine(B, N, k=k, mode=mode, device=0)
     assert eng.scan_geometry()["dynamic_chunk_tiles"] > 0
     eng.load_memory(mem0)
     for t in range(8):
