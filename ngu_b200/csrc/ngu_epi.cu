@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -123,12 +124,17 @@ struct ngu_epi {
     float* r_mapped_dev = nullptr;   // device alias of r_mapped
     // completion of the *_host step: a mapped word the epilogue stores after its last write and the host
     // spins on (a stream synchronize costs a few us more of driver wake-up per step).  Measured and
-    // rejected: reading the inputs in place from mapped memory instead of the staged H2D copy - 1 us
-    // better at 256 x 30k, 25 us worse on small shapes where the PCIe reads land on the critical path.
+    // rejected: (1) reading the inputs in place from mapped memory instead of the staged H2D copy - 1 us
+    // better at 256 x 30k, 25 us worse on small shapes where the PCIe reads land on the critical path;
+    // (2) replaying copy + scan + epilogue as one CUDA graph launch - the enqueue drops from 9.5 to 3.5 us
+    // but the GPU side starts later and loses more (wait 162 -> 174 us at 256 x 30k).
     unsigned int* flag_mapped = nullptr;
     unsigned int* flag_mapped_dev = nullptr;
     unsigned int host_seq = 0;
     bool host_flag_wait = true;      // experiments: NGU_EPI_HOST_PATH=sync -> stream synchronize instead
+    bool host_profile = false;       // NGU_EPI_HOST_PROFILE=1: wall-clock split of ngu_epi_step_host, printed at destroy
+    double prof_us[4] = {0, 0, 0, 0};   // stage-in, enqueue, wait, copy-out
+    long prof_calls = 0;
     // launch geometry
     Variant var{};
     CUtensorMap tmap{};
@@ -366,7 +372,9 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
     CREATE_TRY(cudaHostAlloc(&h->flag_mapped, 64, cudaHostAllocMapped));
     CREATE_TRY(cudaHostGetDevicePointer(&h->flag_mapped_dev, h->flag_mapped, 0));
     *h->flag_mapped = 0u;
+
     if (const char* e = getenv("NGU_EPI_HOST_PATH")) h->host_flag_wait = std::strcmp(e, "sync") != 0;
+    if (const char* e = getenv("NGU_EPI_HOST_PROFILE")) h->host_profile = atoi(e) != 0;
 #undef CREATE_TRY
 
     EpiConsts& c = h->consts;
@@ -389,6 +397,10 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
 
 void ngu_epi_destroy(ngu_epi* h) {
     if (!h) return;
+    if (h->host_profile && h->prof_calls > 0)
+        fprintf(stderr, "[ngu_epi] step_host x%ld: stage-in %.2f us, enqueue %.2f us, wait %.2f us, copy-out %.2f us per call\n",
+                h->prof_calls, h->prof_us[0] / h->prof_calls, h->prof_us[1] / h->prof_calls, h->prof_us[2] / h->prof_calls,
+                h->prof_us[3] / h->prof_calls);
     cudaSetDevice(h->cfg.device);
     if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
     for (cudaEvent_t e : h->t_beg) cudaEventDestroy(e);
@@ -404,6 +416,7 @@ void ngu_epi_destroy(ngu_epi* h) {
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->r_mapped) cudaFreeHost(h->r_mapped);
     if (h->flag_mapped) cudaFreeHost(h->flag_mapped);
+
     delete h;
 }
 
@@ -602,11 +615,16 @@ int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host, 
     if (rc) return rc;
     const size_t B = h->cfg.n_actors;
     cudaStream_t s = h->own_stream;
+    using clk = std::chrono::steady_clock;
+    const bool prof = h->host_profile;
+    clk::time_point t0, t1, t2, t3;
+    if (prof) t0 = clk::now();
     const unsigned int seq = ++h->host_seq;
     const HostFlag hf{h->flag_mapped_dev, seq};
     // one pinned H2D copy carries the step's controllable states and (optionally) the modulators
     std::memcpy(h->pinned, q_host, B * 32 * sizeof(float));
     if (alpha_host) std::memcpy(h->pinned + B * 32, alpha_host, B * sizeof(float));
+    if (prof) t1 = clk::now();
     CU_TRY(h, cudaMemcpyAsync(h->q_stage_dev, h->pinned, B * (alpha_host ? 33 : 32) * sizeof(float),
                               cudaMemcpyHostToDevice, s));
     const float* q_dev = h->q_stage_dev;
@@ -614,14 +632,21 @@ int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host, 
     rc = step_impl(h, q_dev, alpha_host ? q_dev + B * 32 : nullptr, h->r_mapped_dev, h->r_mapped_dev + B, s,
                    h->host_flag_wait ? &hf : nullptr);
     if (rc) return rc;
+    if (prof) t2 = clk::now();
     if (h->host_flag_wait) {
         rc = wait_host_flag(h, seq, s);
         if (rc) return rc;
     } else {
         CU_TRY(h, cudaStreamSynchronize(s));
     }
+    if (prof) t3 = clk::now();
     std::memcpy(r_int_host, h->r_mapped, B * sizeof(float));
     if (r_epi_host) std::memcpy(r_epi_host, h->r_mapped + B, B * sizeof(float));
+    if (prof) {
+        const auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        h->prof_us[0] += us(t0, t1); h->prof_us[1] += us(t1, t2); h->prof_us[2] += us(t2, t3); h->prof_us[3] += us(t3, clk::now());
+        h->prof_calls += 1;
+    }
     return NGU_OK;
 }
 

@@ -77,6 +77,9 @@ class EpisodicEngine:
         self._r_int = torch.empty(self.n_actors, dtype=torch.float32, device=self.device)
         self._r_epi = torch.empty(self.n_actors, dtype=torch.float32, device=self.device)
         self.log_sums = torch.zeros(5, dtype=torch.float64, device=self.device)
+        self._step_host_fn = self._lib.ngu_epi_step_host
+        self._out = np.empty((2, self.n_actors), np.float32)      # step_host result staging (address cached)
+        self._out_ptr = self._out.ctypes.data
 
     # ---- lifetime -----------------------------------------------------------
     def close(self):
@@ -157,22 +160,30 @@ class EpisodicEngine:
         return self._r_int, self._r_epi, self._alpha_out
 
     # ---- host-buffer path (what the drop-in calls with CPU tensors) ---------------
-    def step_host(self, q: np.ndarray, alpha: np.ndarray | None = None):
-        """ngu_epi_step_host: host float32 arrays in, host float32 rewards (r_int, r_epi) out, synchronous."""
-        if not (isinstance(q, np.ndarray) and q.dtype == np.float32 and q.flags.c_contiguous):
-            q = np.ascontiguousarray(q, dtype=np.float32)
-        if q.shape != (self.n_actors, _cabi.DIM):
-            raise ValueError(f"controllable state must be ({self.n_actors}, {_cabi.DIM}), got {q.shape}")
-        a_ptr = None
-        if alpha is not None:
-            if not (isinstance(alpha, np.ndarray) and alpha.dtype == np.float32 and alpha.flags.c_contiguous):
-                alpha = np.ascontiguousarray(alpha, dtype=np.float32)
-            if alpha.shape != (self.n_actors,):
-                raise ValueError(f"alpha must be ({self.n_actors},), got {alpha.shape}")
-            a_ptr = alpha.ctypes.data
-        out = np.empty((2, self.n_actors), np.float32)
-        check(self._lib.ngu_epi_step_host(self._h, q.ctypes.data, a_ptr, out.ctypes.data,
-                                          out.ctypes.data + 4 * self.n_actors), self._h)
+    def _host_ptr(self, x, shape, what):
+        """Address of a host float32 C-contiguous array (CPU torch tensor or numpy array) of `shape`;
+        anything else is converted first.  Returns (address, keep-alive object)."""
+        if type(x) is torch.Tensor:
+            if x.device.type != "cpu" or x.dtype != torch.float32 or not x.is_contiguous():
+                x = x.detach().to(device="cpu", dtype=torch.float32).contiguous()
+            if tuple(x.shape) != shape:
+                raise ValueError(f"{what} must be {shape}, got {tuple(x.shape)}")
+            return x.data_ptr(), x              # 0.1 us, where ndarray.ctypes.data costs 1.8 us
+        if type(x) is not np.ndarray or x.dtype != np.float32 or not x.flags.c_contiguous:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.shape != shape:
+            raise ValueError(f"{what} must be {shape}, got {x.shape}")
+        return x.ctypes.data, x
+
+    def step_host(self, q, alpha=None):
+        """ngu_epi_step_host: host float32 buffers in (CPU torch tensors or numpy arrays; torch tensors are
+        the cheaper to pass), host float32 rewards (r_int, r_epi) out as fresh numpy arrays, synchronous."""
+        q_ptr, _q = self._host_ptr(q, (self.n_actors, _cabi.DIM), "controllable state")
+        a_ptr, _a = (None, None) if alpha is None else self._host_ptr(alpha, (self.n_actors,), "alpha")
+        rc = self._step_host_fn(self._h, q_ptr, a_ptr, self._out_ptr, self._out_ptr + 4 * self.n_actors)
+        if rc:
+            check(rc, self._h)
+        out = self._out.copy()
         return out[0], out[1]
 
     def reset_host(self, done: np.ndarray):
