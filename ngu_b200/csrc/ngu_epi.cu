@@ -97,7 +97,9 @@ struct ngu_epi {
     double* rank_sums = nullptr;     // [2k+1]
     double* log_sums = nullptr;      // [5]
     u64* actor_state = nullptr;              // [B][2] per actor {published floor, arrived tiles << 32 | reserved candidates}
-    unsigned int* sched_ctr = nullptr;       // [4] dynamic chunk counter, finished-warp counter, launch epoch
+    unsigned int* sched_ctr = nullptr;       // [8] dynamic chunk counter, finished-warp counter, launch epoch, merge-job counter, leftovers
+    int32_t* leftover = nullptr;             // [B] merge jobs given up by their first taker (scan_topk.cuh: merge_job)
+    long long poll_limit_cycles = 4000000;   // ~2 ms without progress; NGU_EPI_DEBUG_POLL_LIMIT overrides (tests: 0)
     ScanSched sched{};
     double sched_static_frac = 0.6;          // share of the tiles handed out statically (experiments: NGU_EPI_SCHED=frac,c2)
     int sched_c2 = 16;                       // tiles per dynamic chunk
@@ -346,9 +348,11 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
     CREATE_TRY(cudaMalloc(&h->log_sums, 8 * sizeof(double)));
     CREATE_TRY(cudaMalloc(&h->actor_state, static_cast<size_t>(B) * 2 * sizeof(u64)));
     CREATE_TRY(cudaMemset(h->actor_state, 0, static_cast<size_t>(B) * 2 * sizeof(u64)));
-    CREATE_TRY(cudaMalloc(&h->sched_ctr, 4 * sizeof(unsigned int)));
+    CREATE_TRY(cudaMalloc(&h->leftover, static_cast<size_t>(B) * sizeof(int32_t)));
+    if (const char* e = getenv("NGU_EPI_DEBUG_POLL_LIMIT")) h->poll_limit_cycles = atoll(e);
+    CREATE_TRY(cudaMalloc(&h->sched_ctr, 8 * sizeof(unsigned int)));
     {
-        unsigned int init[4] = {0u, 0u, 1u, 0u};         // first launch epoch = 1
+        unsigned int init[8] = {0u, 0u, 1u, 0u, 0u, 0u, 0u, 0u};   // first launch epoch = 1
         if (const char* e = getenv("NGU_EPI_DEBUG_EPOCH")) init[2] = static_cast<unsigned int>(strtoul(e, nullptr, 0));   // tests: cross the wrap
         if (init[2] == 0u) init[2] = 1u;
         CREATE_TRY(cudaMemcpy(h->sched_ctr, init, sizeof init, cudaMemcpyHostToDevice));
@@ -411,7 +415,7 @@ void ngu_epi_destroy(ngu_epi* h) {
     cudaFree(h->inbox);
     if (h->owns_memory) cudaFree(h->memory);
     cudaFree(h->cand); cudaFree(h->topk_d2); cudaFree(h->topk_idx); cudaFree(h->dist);
-    cudaFree(h->rank_sums); cudaFree(h->log_sums); cudaFree(h->state); cudaFree(h->actor_state); cudaFree(h->sched_ctr); cudaFree(h->plan_dev); cudaFree(h->timeline);
+    cudaFree(h->rank_sums); cudaFree(h->log_sums); cudaFree(h->state); cudaFree(h->actor_state); cudaFree(h->sched_ctr); cudaFree(h->leftover); cudaFree(h->plan_dev); cudaFree(h->timeline);
     cudaFree(h->q_stage_dev); cudaFree(h->done_stage_dev);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->r_mapped) cudaFreeHost(h->r_mapped);
@@ -453,6 +457,7 @@ static int launch_scan(ngu_epi* h, const float* q_dev, cudaStream_t s) {
     sp.largest = h->consts.largest; sp.sqrt_dist = h->consts.sqrt_dist; sp.neg_zero2 = kNegZero2;
     sp.tiles_per_actor = h->tiles_per_actor;
     sp.max_cand = h->max_cand; sp.sched = h->sched; sp.sched_ctr = h->sched_ctr;
+    sp.leftover = h->leftover; sp.poll_limit_cycles = h->poll_limit_cycles;
     sp.actor_state = h->actor_state;
     sp.timeouts = reinterpret_cast<unsigned long long*>(&h->state->exchange_timeouts);
     sp.topk_d2 = h->topk_d2; sp.topk_idx = h->topk_idx; sp.dist = h->dist;

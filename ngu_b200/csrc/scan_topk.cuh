@@ -99,8 +99,11 @@ struct ScanParams {
     int32_t sqrt_dist;       // 1: dist = sqrt(d2) (reference), 0: dist = d2 (paper)
     unsigned long long neg_zero2;   // (-0.0f, -0.0f): opaque addend of the packed squares, see f2_sq
     ScanSched sched;
-    unsigned int* sched_ctr;       // [0] dynamic chunk counter, [1] finished warps, [3] merge-job counter (zero between
-                                   // launches), [2] launch epoch = tag of this launch's candidates and floors (never 0)
+    unsigned int* sched_ctr;       // [0] dynamic chunk counter, [1] finished warps, [3] merge-job counter, [4] leftover
+                                   // merge jobs (all zero between launches), [2] launch epoch = tag of this launch's
+                                   // candidates and floors (never 0)
+    int32_t* leftover;             // [B] actors whose merge job was given up (see merge_job), merged by the last warp
+    long long poll_limit_cycles;   // a merge job that sees no progress for this long is given up (0: at once - tests)
     unsigned long long* timeouts;  // incremented if a merge gave up waiting for a candidate (must stay 0)
     u64* actor_state;              // [B][2]: {floor, ctr} (16 bytes, so that one bulk copy can fetch the floor)
                                    //   floor: epoch << 32 | hi word of a key known to be <= the final k-th best
@@ -303,8 +306,15 @@ __device__ __forceinline__ void consume_lists(const ScanParams& p, const u64* ca
 // count finally completes, only the last few candidates are left to read - one round trip after the
 // last tile instead of a whole merge.  Nothing is merged inside the streaming loop, so the loop
 // carries no merge registers.
-__device__ __forceinline__ void merge_job(const ScanParams& p, int actor, uint32_t tag, int lane, uint32_t stage /* 8 KB smem */,
-                                          unsigned long long* tl /* debug timeline record or null */) {
+// Waiting is BOUNDED.  A job polls for tiles that other warps still have to scan; should the grid ever not
+// be fully co-resident (an SM limit imposed from outside, a long-running kernel of another stream holding
+// shared memory), resident warps would otherwise sit polling for tiles of CTAs that cannot launch until
+// they leave.  A job that sees no progress for poll_limit_cycles is therefore put on a leftover list and its
+// warp moves on and exits; the LAST warp of the launch to finish - by then every tile has been scanned -
+// merges the leftovers (`may_give_up` = false: nothing left to wait for but stores in flight).
+// Returns false if the job was given up.
+__device__ __forceinline__ bool merge_job(const ScanParams& p, int actor, uint32_t tag, int lane, uint32_t stage /* 8 KB smem */,
+                                          bool may_give_up, unsigned long long* tl /* debug timeline record or null */) {
     const int k = p.k;
     u64* ctr = actor_ctr(p, actor);
     const u64* cand = p.cand + static_cast<int64_t>(actor) * p.max_cand * 2;
@@ -312,6 +322,7 @@ __device__ __forceinline__ void merge_job(const ScanParams& p, int actor, uint32
     m.reset();
     int done = 0, spins = 0;
     uint32_t n = 0;
+    long long t_progress = clock64();
     const unsigned long long dbg_t0 = tl ? globaltimer_ns() : 0ull;
     for (;;) {
         // Any floor published during this launch is a valid lower bound of the final k-th best, and it
@@ -324,16 +335,26 @@ __device__ __forceinline__ void merge_job(const ScanParams& p, int actor, uint32
         m.floor = umax64(m.floor, floor_key(fw, tag));
         m.thr = umax64(m.thr, m.floor);
         const int avail = static_cast<int>(n);
+        if (avail > done) t_progress = clock64();
         consume_candidates(p, cand, done, avail, tag, lane, stage, m);
         done = avail;
         if (complete) break;
+        const int waited_too_long = __shfl_sync(kFull, clock64() - t_progress >= p.poll_limit_cycles ? 1 : 0, 0);   // lane 0 decides
+        if (may_give_up && waited_too_long) {
+            if (lane == 0) {
+                p.leftover[atomicAdd(p.sched_ctr + 4, 1u)] = actor;
+                __threadfence();                          // ... before this warp counts itself finished
+            }
+            return false;
+        }
         if (++spins > kLLSpinLimit) { if (lane == 0) atomicAdd(p.timeouts, 1ull); break; }
     }
     __syncwarp();
     if (lane == 0) *ctr = 0ull;                           // re-arm for the next launch: every arrival has been performed
     if (tl && lane == 0) { tl[5] = dbg_t0; tl[6] = n; tl[7] = globaltimer_ns(); }   // merge job: start, candidates, end
-    if (n == kWrittenDirectly || (p.debug & 8)) return;
+    if (n == kWrittenDirectly || (p.debug & 8)) return true;
     write_knn(knn_out(p, actor), k, knn_flags(p), m.lkey, lane);
+    return true;
 }
 
 // STATIC schedules (small shapes: every warp owns exactly one chunk of s1 tiles).  These are bound by
@@ -681,15 +702,22 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
             if (lane == 0) job = static_cast<int>(atomicAdd(p.sched_ctr + 3, 1u));
             job = __shfl_sync(kFull, job, 0);
             if (job >= p.n_actors) break;
-            merge_job(p, job, tag, lane, my_tiles, tl_rec);
+            merge_job(p, job, tag, lane, my_tiles, true, tl_rec);
         }
     }
     else if (top.lkey == 0x1234567ull) p.topk_d2[0] = 0.f;   // keep the experiment's loads alive
-    if (lane == 0) {
-        // the last working warp re-arms the scheduler for the next launch (every other warp has
-        // consumed the result of its last counter atomic before it got here)
-        if (atomicAdd(p.sched_ctr + 1, 1u) == static_cast<unsigned>(workers) - 1u) {
-            p.sched_ctr[0] = 0u; p.sched_ctr[1] = 0u; p.sched_ctr[3] = 0u;
+    // The last working warp of the launch merges the jobs that were given up (normally none) and re-arms the
+    // scheduler for the next launch (every other warp has consumed the result of its last counter atomic
+    // before it got here).
+    unsigned last = 0;
+    if (lane == 0) last = atomicAdd(p.sched_ctr + 1, 1u) == static_cast<unsigned>(workers) - 1u ? 1u : 0u;
+    last = __shfl_sync(kFull, last, 0);
+    if (last) {
+        __threadfence();
+        const int n_left = static_cast<int>(__ldcg(p.sched_ctr + 4));
+        for (int i = 0; i < n_left; ++i) merge_job(p, __ldcg(p.leftover + i), tag, lane, my_tiles, false, nullptr);
+        if (lane == 0) {
+            p.sched_ctr[0] = 0u; p.sched_ctr[1] = 0u; p.sched_ctr[3] = 0u; p.sched_ctr[4] = 0u;
             uint32_t next = tag + 1u;                      // next launch's epoch
             if (next == 0u) {                              // wrapped: 0 is never a valid tag, and floors of the old
                 next = 1u;                                 // cycle would out-rank every new one in the atomicMax

@@ -154,13 +154,18 @@ def test_schedule_partitions_the_tile_space(cuda_device, monkeypatch, B, N, sche
     eng.close()
 
 
-@pytest.mark.parametrize("sched,epoch,k,mode", [("0.5,2,1", None, 10, "reference"), ("0.0,3,1", None, 10, "reference"),
-                                                 ("0.6,16,1", None, 10, "reference"), ("0.5,2,1", "0xFFFFFFFD", 10, "reference"),
-                                                 ("0.5,2,1", None, 32, "reference"), ("0.3,4,1", None, 1, "reference"),
-                                                 ("0.5,2,1", None, 10, "paper")])
-def test_dynamic_schedule_vs_oracle(cuda_device, monkeypatch, sched, epoch, k, mode):
+@pytest.mark.parametrize("sched,epoch,k,mode,poll", [
+    ("0.5,2,1", None, 10, "reference", None), ("0.0,3,1", None, 10, "reference", None),
+    ("0.6,16,1", None, 10, "reference", None), ("0.5,2,1", "0xFFFFFFFD", 10, "reference", None),
+    ("0.5,2,1", None, 32, "reference", None), ("0.3,4,1", None, 1, "reference", None),
+    ("0.5,2,1", None, 10, "paper", None), ("0.5,2,1", None, 10, "reference", "0"), ("0.6,16,1", None, 10, "reference", "0")])
+def test_dynamic_schedule_vs_oracle(cuda_device, monkeypatch, sched, epoch, k, mode, poll):
     """Many short runs per actor (hundreds of flushes, floors, in-flight candidates, merge jobs) at a size
-    the oracle checks in full; `epoch` starts the launch epoch just below its 32-bit wrap."""
+    the oracle checks in full; `epoch` starts the launch epoch just below its 32-bit wrap; `poll` = "0"
+    makes every merge job that is not complete at its first look give up, so that the last warp of the
+    launch merges the leftovers (the path that keeps a not fully co-resident grid from deadlocking)."""
+    if poll is not None:
+        monkeypatch.setenv("NGU_EPI_DEBUG_POLL_LIMIT", poll)
     from ngu_b200.engine import EpisodicEngine
     from oracle.episodic_oracle import EpisodicOracle
     monkeypatch.setenv("NGU_EPI_SCHED", sched)
