@@ -99,6 +99,7 @@ struct ngu_epi {
     u64* actor_state = nullptr;              // [B][2] per actor {published floor, arrived tiles << 32 | reserved candidates}
     unsigned int* sched_ctr = nullptr;       // [8] dynamic chunk counter, finished-warp counter, launch epoch, merge-job counter, leftovers
     int32_t* leftover = nullptr;             // [B] merge jobs given up by their first taker (scan_topk.cuh: merge_job)
+    int prefetch_tiles = 4;                  // experiments: NGU_EPI_PREFETCH_TILES
     long long poll_limit_cycles = 4000000;   // ~2 ms without progress; NGU_EPI_DEBUG_POLL_LIMIT overrides (tests: 0)
     ScanSched sched{};
     double sched_static_frac = 0.6;          // share of the tiles handed out statically (experiments: NGU_EPI_SCHED=frac,c2)
@@ -350,6 +351,7 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
     CREATE_TRY(cudaMemset(h->actor_state, 0, static_cast<size_t>(B) * 2 * sizeof(u64)));
     CREATE_TRY(cudaMalloc(&h->leftover, static_cast<size_t>(B) * sizeof(int32_t)));
     if (const char* e = getenv("NGU_EPI_DEBUG_POLL_LIMIT")) h->poll_limit_cycles = atoll(e);
+    if (const char* e = getenv("NGU_EPI_PREFETCH_TILES")) h->prefetch_tiles = atoi(e) < 0 ? 0 : (atoi(e) > kMaxPrefetchTiles ? kMaxPrefetchTiles : atoi(e));
     CREATE_TRY(cudaMalloc(&h->sched_ctr, 8 * sizeof(unsigned int)));
     {
         unsigned int init[8] = {0u, 0u, 1u, 0u, 0u, 0u, 0u, 0u};   // first launch epoch = 1
@@ -457,7 +459,7 @@ static int launch_scan(ngu_epi* h, const float* q_dev, cudaStream_t s) {
     sp.largest = h->consts.largest; sp.sqrt_dist = h->consts.sqrt_dist; sp.neg_zero2 = kNegZero2;
     sp.tiles_per_actor = h->tiles_per_actor;
     sp.max_cand = h->max_cand; sp.sched = h->sched; sp.sched_ctr = h->sched_ctr;
-    sp.leftover = h->leftover; sp.poll_limit_cycles = h->poll_limit_cycles;
+    sp.leftover = h->leftover; sp.poll_limit_cycles = h->poll_limit_cycles; sp.prefetch_tiles = h->prefetch_tiles;
     sp.actor_state = h->actor_state;
     sp.timeouts = reinterpret_cast<unsigned long long*>(&h->state->exchange_timeouts);
     sp.topk_d2 = h->topk_d2; sp.topk_idx = h->topk_idx; sp.dist = h->dist;

@@ -102,6 +102,7 @@ struct ScanParams {
     unsigned int* sched_ctr;       // [0] dynamic chunk counter, [1] finished warps, [3] merge-job counter, [4] leftover
                                    // merge jobs (all zero between launches), [2] launch epoch = tag of this launch's
                                    // candidates and floors (never 0)
+    int32_t prefetch_tiles;        // tiles per warp prefetched into L2 before the grid dependency resolves
     int32_t* leftover;             // [B] actors whose merge job was given up (see merge_job), merged by the last warp
     long long poll_limit_cycles;   // a merge job that sees no progress for this long is given up (0: at once - tests)
     unsigned long long* timeouts;  // incremented if a merge gave up waiting for a candidate (must stay 0)
@@ -113,7 +114,7 @@ struct ScanParams {
     float* dist;             // [B][k]
     unsigned long long* timeline;  // debug (tools/scan_timeline.py): per warp {start, first tile, scan end, flush end, smid} (8 words), or null
     int32_t debug;           // experiments only (NGU_EPI_DEBUG_SCAN): 1 = no top-k offers, 2 = no distance math, 4 = no flush,
-                             // 8 = no merge, 16 = no floor seeding
+                             // 8 = no merge, 16 = no floor seeding, 32 = no L2 prefetch before the grid dependency
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -186,6 +187,7 @@ __device__ __forceinline__ u64 ld_volatile_u64(const u64* src) {
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
     return v;
 }
+constexpr int kMaxPrefetchTiles = 16;
 constexpr int kLLSpinLimit = 1 << 22;   // ~ seconds; a healthy wait is about one tile time
 // floor word -> the largest key that is certainly NOT needed (0 = no floor)
 __device__ __forceinline__ u64 floor_key(u64 floor_word, uint32_t tag) {
@@ -446,6 +448,10 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// TMA prefetch of one tile into L2 (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -543,25 +549,39 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
     const ScanSched& sc = p.sched;
     if (gw >= sc.n_chunks) return;  // whole warp exits together; no CTA-wide barriers below
 
+    const int tpa = p.tiles_per_actor;
+    const int N = p.capacity;
+    int pt, pte;                       // current chunk: next tile to load, end
+    chunk_range(sc, gw, pt, pte);      // first chunk is static: no atomic before the first load
+    int pb = pt / tpa;                 // actor / tile-in-actor of `pt`
+    int pti = pt - pb * tpa;
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) mbar_init(my_bars + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // While the predecessor (the previous step's epilogue) is still running, pull this warp's first tiles
+        // into L2: the CTA is resident but may not touch the memory's CONTENT before the grid dependency
+        // resolves (the epilogue is appending a row) - a prefetch does not, and L2 being the coherence point
+        // the real loads below still see that row.  ~28 MB of HBM traffic leave the step's critical path.
+        if (!(p.debug & 32)) {
+            int fb = pb, fti = pti;
+#pragma unroll 1
+            for (int s = 0; s < p.prefetch_tiles; ++s) {
+                if (pt + s < pte) {
+                    tma_prefetch_2d(&tmap, 0, fb * N + fti * Cfg::kTileRows);
+                    if (++fti == tpa) { fti = 0; ++fb; }
+                }
+            }
+        }
     }
     __syncwarp();
     pdl_wait();   // predecessor (previous step's epilogue: append, readers of dist/topk) is complete
 
-    const int tpa = p.tiles_per_actor;
-    const int N = p.capacity;
     const uint64_t policy = l2_evict_first_policy();
     const uint32_t tag = __ldcg(p.sched_ctr + 2);   // launch epoch (first needed at the first flush)
 
     // ---- producer (lane 0): walks this warp's chunks STAGES tiles ahead of the consumer ----
-    int pt, pte;                       // current chunk: next tile to load, end
-    chunk_range(sc, gw, pt, pte);      // first chunk is static: no atomic before the first load
-    int pb = pt / tpa;                 // actor / tile-in-actor of `pt`
-    int pti = pt - pb * tpa;
     int pending = sc.n_chunks;         // next chunk index, fetched one chunk ahead
     int last_pb = -1;                  // actor of the tile issued last: a change = the consumer starts a new run there
     bool live = true;
