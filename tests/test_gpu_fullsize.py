@@ -111,3 +111,37 @@ def test_long_trajectory_64x5000_vs_oracle(cuda_device):
         eng.reset_host(done)
     assert np.array_equal(eng.dump_memory(), orc.memory)
     eng.close()
+
+
+def test_256x30k_zero_memory_all_ties(cuda_device):
+    """The state every real run starts in: an all-zero memory, every slot tying with every other (the
+    reference's unfilled slots are real neighbours).  Ties must resolve to the lowest slots across the
+    hundreds of runs the dynamic schedule cuts an actor into; three steps so that the appended rows and a
+    reset take part.  Checked for every actor against the plain-C oracle."""
+    from ngu_b200.engine import EpisodicEngine
+    from oracle import c_oracle
+    B, N, k = 256, 30000, 10
+    eng = EpisodicEngine(B, N, k=k, device=0)
+    assert eng.scan_geometry()["dynamic_chunk_tiles"] > 0
+    g = torch.Generator(device="cuda").manual_seed(3)
+    mem = np.zeros((N, B, 32), np.float32)
+    for t in range(3):
+        q = torch.randn(B, 32, device="cuda", generator=g)
+        if t == 1:
+            q[7] = 0.0                                   # distance 0 to every zero slot, > 0 to the appended one
+        eng.step(q, None)
+        d2, idx = eng.topk()
+        qc = q.cpu().numpy()
+        for lo in range(0, B, 64):
+            sub = slice(lo, lo + 64)
+            oi, od = c_oracle.scan_topk(np.ascontiguousarray(mem[:, sub]), qc[sub], k, True)
+            assert np.array_equal(oi.T, idx[sub]), f"step {t}, actors {lo}..{lo + 63}: kNN slots differ"
+            assert np.array_equal(od.T.view(np.uint32), d2[sub].view(np.uint32))
+        mem[t] = qc                                      # insert_state at the shared cursor
+        if t == 0:
+            done = torch.zeros(B, dtype=torch.bool)
+            done[[5, 100]] = True
+            eng.reset(done)
+            mem[:, [5, 100]] = 0.0
+    assert eng.get_state()["exchange_timeouts"] == 0
+    eng.close()
