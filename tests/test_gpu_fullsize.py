@@ -145,3 +145,41 @@ def test_256x30k_zero_memory_all_ties(cuda_device):
             mem[:, [5, 100]] = 0.0
     assert eng.get_state()["exchange_timeouts"] == 0
     eng.close()
+
+
+def test_soak_dynamic_vs_static_schedule_bit_identical(cuda_device, monkeypatch):
+    """1500 steps at 256 x 30k: the dynamic schedule (chunk counter, fence-free candidate publication,
+    floors, incremental merge jobs) and the static one (deterministic slots, last arriver merges) are two
+    independent routes to the same k-NN, so their slots, d^2, rewards, memories and running statistics must
+    agree bit for bit on every step - a soak for rare orderings (in-flight candidates, epoch tags, counter
+    re-arming) that short trajectories do not hit."""
+    from ngu_b200.engine import EpisodicEngine
+    B, N = 256, 30000
+    dyn = EpisodicEngine(B, N, device=0)
+    monkeypatch.setenv("NGU_EPI_SCHED", "1.0,0")
+    sta = EpisodicEngine(B, N, device=0)
+    assert dyn.scan_geometry()["dynamic_chunk_tiles"] > 0 and sta.scan_geometry()["dynamic_chunk_tiles"] == 0
+    g = torch.Generator(device="cuda").manual_seed(17)
+    dyn._memory.normal_(generator=g)
+    dyn._memory[:, 20000:] = 0.0                          # a third of every ring still unfilled: ties
+    sta._memory.copy_(dyn._memory)
+    for t in range(1500):
+        q = torch.randn(B, 32, device="cuda", generator=g)
+        a = 1.0 + 2.0 * torch.randn(B, device="cuda", generator=g)
+        r1, e1 = dyn.step(q, a)
+        r2, e2 = sta.step(q, a)
+        if t % 50 == 0 or t > 1480:
+            assert torch.equal(r1, r2) and torch.equal(e1, e2), f"step {t}: rewards differ"
+            (d2a, ia), (d2b, ib) = dyn.topk(), sta.topk()
+            assert np.array_equal(ia, ib) and np.array_equal(d2a.view(np.uint32), d2b.view(np.uint32)), f"step {t}"
+        if t % 97 == 5:
+            done = torch.rand(B, device="cuda", generator=g) < 0.05
+            dyn.reset(done)
+            sta.reset(done)
+    assert torch.equal(dyn._memory, sta._memory)
+    s1, s2 = dyn.get_state(), sta.get_state()
+    assert s1["exchange_timeouts"] == 0 and s2["exchange_timeouts"] == 0
+    for key in ("ed_count", "cursor", "steps", "epi_mean", "intr_mean"):
+        assert s1[key] == s2[key], key
+    assert np.array_equal(s1["ed_mean"], s2["ed_mean"]) and np.array_equal(s1["ed_var"], s2["ed_var"])
+    dyn.close(); sta.close()
