@@ -212,6 +212,10 @@ int ngu_epi_scan_geometry(const ngu_epi* h, int32_t out[8]);
  * schedule, in units of tiles of tile_rows memory slots over the linear space actor * tiles_per_actor +
  * tile; the ranges of all chunks partition that space (tests/test_gpu_parity.py). */
 int ngu_epi_debug_chunk(const ngu_epi* h, int32_t idx, int32_t out[2]);
+/* The same plan WITHOUT a handle or a GPU (host logic only; the CPU test suite checks the partition for
+ * many shapes): geo[8] as ngu_epi_scan_geometry for a device with `sm_count` SMs; chunks (may be NULL)
+ * receives 2 * geo[7] ints, [first tile, end tile) per chunk; max_chunks = capacity of `chunks` in chunks. */
+int ngu_epi_plan_host(const ngu_epi_cfg* cfg, int32_t sm_count, int32_t geo[8], int32_t* chunks, int32_t max_chunks);
 
 /* Measurement aid (bench.py "roofline"): bracket the next `max_calls` launches of
  * the scan kernel (kernel A alone, not the merge) with CUDA events on the launching

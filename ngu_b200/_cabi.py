@@ -66,6 +66,7 @@ SYMBOLS = {
     "ngu_epi_launch_count": (C.c_int64, [_P]),
     "ngu_epi_scan_geometry": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "ngu_epi_debug_chunk": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32)]),
+    "ngu_epi_plan_host": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), _P, C.c_int32]),
     "ngu_epi_debug_timeline": (C.c_int, [_P, _P, C.c_int32]),
     "ngu_epi_scan_timing_begin": (C.c_int, [_P, C.c_int32]),
     "ngu_epi_scan_timing_end": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),

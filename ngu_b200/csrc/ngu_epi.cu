@@ -232,6 +232,17 @@ void plan_geometry(ngu_epi* h) {
     h->max_cand = ((h->tiles_per_actor + min_chunk - 1) / min_chunk + 3) * h->cfg.k;
 }
 
+void apply_sched_env(ngu_epi* h) {
+    if (const char* e = getenv("NGU_EPI_SCHED")) {   // experiments and tests: "static_frac,c2[,min_avg_tiles[,min_tiles_per_warp]]"
+        double f = 0.6; int c2 = 16, mn = kDynMinAvgTilesDefault, mt = kMinTilesPerWarp;
+        const int got = sscanf(e, "%lf,%d,%d,%d", &f, &c2, &mn, &mt);
+        if (got >= 1 && f >= 0.0) h->sched_static_frac = f;
+        if (got >= 2) h->sched_c2 = c2;
+        if (got >= 3 && mn >= 0) h->sched_min_avg = mn;
+        if (got >= 4 && mt >= 1) h->sched_min_tiles = mt;
+    }
+}
+
 int default_state(ngu_epi* h) {
     ngu_epi_state s;
     std::memset(&s, 0, sizeof s);
@@ -318,14 +329,7 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
     }
     if (const char* e = getenv("NGU_EPI_DEBUG_PHASES")) h->debug_phase_mask = atoi(e);
     if (const char* e = getenv("NGU_EPI_DEBUG_SCAN")) h->debug_scan = atoi(e);
-    if (const char* e = getenv("NGU_EPI_SCHED")) {   // experiments and tests: "static_frac,c2[,min_avg_tiles[,min_tiles_per_warp]]"
-        double f = 0.6; int c2 = 16, mn = kDynMinAvgTilesDefault, mt = kMinTilesPerWarp;
-        const int got = sscanf(e, "%lf,%d,%d,%d", &f, &c2, &mn, &mt);
-        if (got >= 1 && f >= 0.0) h->sched_static_frac = f;
-        if (got >= 2) h->sched_c2 = c2;
-        if (got >= 3 && mn >= 0) h->sched_min_avg = mn;
-        if (got >= 4 && mt >= 1) h->sched_min_tiles = mt;
-    }
+    apply_sched_env(h);
     plan_geometry(h);
 
     const int B = cfg->n_actors, k = cfg->k;
@@ -816,6 +820,30 @@ int ngu_epi_debug_timeline(ngu_epi* h, uint64_t* out_host, int32_t max_warps) {
     CU_TRY(h, cudaDeviceSynchronize());
     CU_TRY(h, cudaMemcpy(out_host, h->timeline, static_cast<size_t>(n) * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return n;
+}
+
+int ngu_epi_plan_host(const ngu_epi_cfg* cfg, int32_t sm_count, int32_t geo[8], int32_t* chunks, int32_t max_chunks) {
+    if (!cfg || !geo || sm_count < 1) return NGU_EINVAL;
+    if (cfg->n_actors < 1 || cfg->capacity < 1 || cfg->k < 1 || cfg->k > NGU_EPI_MAX_K || cfg->scan_variant < 0 ||
+        cfg->scan_variant >= kNumVariants || static_cast<int64_t>(cfg->n_actors) * cfg->capacity + 256 >= (1ll << 31))
+        return NGU_EINVAL;
+    ngu_epi h;                        // host-side planning only: no CUDA call is made
+    h.cfg = *cfg;
+    h.sm_count = sm_count;
+    h.var = kVariants[cfg->scan_variant];
+    if (cfg->scan_ctas_per_sm > 0) h.var.ctas_per_sm = cfg->scan_ctas_per_sm;
+    apply_sched_env(&h);
+    plan_geometry(&h);
+    ngu_epi_scan_geometry(&h, geo);
+    if (chunks) {
+        if (max_chunks < h.sched.n_chunks) return NGU_EINVAL;
+        for (int i = 0; i < h.sched.n_chunks; ++i) {
+            int t = 0, te = 0;
+            chunk_range(h.sched, i, t, te);
+            chunks[2 * i] = t; chunks[2 * i + 1] = te;
+        }
+    }
+    return NGU_OK;
 }
 
 int ngu_epi_debug_chunk(const ngu_epi* h, int32_t idx, int32_t out[2]) {

@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -98,3 +99,46 @@ def test_actor_partition():
     from ngu_b200.sharding import actor_partition
     assert actor_partition(256, 8) == [0, 32, 64, 96, 128, 160, 192, 224, 256]
     assert actor_partition(10, 4) == [0, 3, 6, 8, 10]
+
+
+@pytest.mark.parametrize("sched", [None, "0.5,2,1", "0.0,3,1", "0.3,8,1,2", "1.0,0"])
+def test_scan_schedule_partitions_the_tile_space_host_side(lib, monkeypatch, sched):
+    """Host logic of the scan kernel's work schedule (plan_geometry + chunk_range, no GPU needed): for
+    many shapes, SM counts and kernel geometries every tile is handed out exactly once, the grid is one
+    wave at most, and the statically owned chunks are the first ones."""
+    import ctypes as C
+    from ngu_b200._cabi import NguEpiCfg
+    if sched:
+        monkeypatch.setenv("NGU_EPI_SCHED", sched)
+    else:
+        monkeypatch.delenv("NGU_EPI_SCHED", raising=False)
+    rng = np.random.default_rng(0)
+    shapes = [(256, 30000), (1024, 30000), (1, 30000), (64, 5000), (37, 777), (3, 10), (5000, 33), (1, 10), (4096, 1000)]
+    shapes += [(int(rng.integers(1, 600)), int(rng.integers(10, 40000))) for _ in range(12)]
+    ctas = {0: 2, 1: 1, 2: 1, 3: 1, 4: 3, 5: 3, 6: 1, 7: 1}
+    warps = {0: 8, 1: 8, 2: 8, 3: 16, 4: 8, 5: 4, 6: 8, 7: 4}
+    for (B, N) in shapes:
+        for sms, variant in [(148, 0), (132, 0), (148, 2), (148, 4), (20, 5)]:
+            cfg = NguEpiCfg(n_actors=B, capacity=N, dim=32, k=10, mode=0, device=0, kernel_epsilon=1e-4,
+                            cluster_distance=0.008, pseudo_counts=1e-3, max_similarity=8.0, max_reward_scale=5.0,
+                            reserved0=0.0, prior_count=10.0, scan_ctas_per_sm=0, scan_variant=variant)
+            geo = (C.c_int32 * 8)()
+            assert lib.ngu_epi_plan_host(C.byref(cfg), sms, geo, None, 0) == 0
+            grid, block, _, s1, _, tile_rows, c2, n_chunks = list(geo)
+            chunks = (C.c_int32 * (2 * n_chunks))()
+            assert lib.ngu_epi_plan_host(C.byref(cfg), sms, geo, chunks, n_chunks) == 0
+            tpa = -(-N // tile_rows)
+            cover = np.zeros(B * tpa + 1, np.int64)
+            ch = np.frombuffer(chunks, dtype=np.int32).reshape(n_chunks, 2)
+            assert (ch[:, 0] >= 0).all() and (ch[:, 0] <= ch[:, 1]).all() and (ch[:, 1] <= B * tpa).all()
+            np.add.at(cover, ch[:, 0], 1)
+            np.add.at(cover, ch[:, 1], -1)
+            assert (np.cumsum(cover)[:-1] == 1).all(), (B, N, sms, variant, "tiles not covered exactly once")
+            assert block == 32 * warps[variant] and 1 <= grid <= sms * ctas[variant]
+            n_warps = grid * warps[variant]
+            if c2 == 0:                                    # static schedule: one chunk per warp, nobody idle by design
+                assert n_chunks <= n_warps and s1 >= 1
+            else:                                          # dynamic: a full wave, the first n_warps chunks are the static ones
+                assert grid == sms * ctas[variant] and c2 >= 1
+                assert (ch[:min(n_warps, n_chunks), 1] - ch[:min(n_warps, n_chunks), 0] <= max(s1, c2)).all()
+    assert lib.ngu_epi_plan_host(None, 148, None, None, 0) != 0
