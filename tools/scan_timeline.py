@@ -6,7 +6,7 @@ import numpy as np, torch
 from ngu_b200.engine import EpisodicEngine
 
 pct = lambda x: [round(float(v), 2) for v in np.percentile(x, [0, 10, 50, 90, 100])]
-CASES = [(256, 30000, 0, d, sc) for sc in ("0.6,16", "0.6,8", "1.0,0") for d in (0, 1, 16)]
+CASES = [(256, 30000, 0, d, "0.6,16") for d in (0, 1, 3, 7, 4, 32, 0)]
 for B, N, variant, dbg, sched in CASES:
     os.environ["NGU_EPI_DEBUG_SCAN"] = str(dbg)
     os.environ["NGU_EPI_SCHED"] = sched
