@@ -183,3 +183,41 @@ def test_soak_dynamic_vs_static_schedule_bit_identical(cuda_device, monkeypatch)
         assert s1[key] == s2[key], key
     assert np.array_equal(s1["ed_mean"], s2["ed_mean"]) and np.array_equal(s1["ed_var"], s2["ed_var"])
     dyn.close(); sta.close()
+
+
+def test_back_to_back_steps_overlap_vs_oracle(cuda_device):
+    """40 steps enqueued back to back (no host synchronisation in between) at a shape that takes the
+    dynamic schedule: every scan is programmatically launched behind the previous epilogue and prefetches
+    its first tiles into L2 while that epilogue is still appending - the appended rows (cursor 0..39, i.e.
+    inside prefetched tiles) must nevertheless be seen by the following steps.  Every step's rewards are
+    kept on the device and compared with the oracle afterwards, as are the memory and the trackers."""
+    from ngu_b200.engine import EpisodicEngine
+    from oracle.episodic_oracle import EpisodicOracle
+    B, N, k, steps = 64, 30000, 10, 40
+    rng = np.random.default_rng(21)
+    mem0 = rng.standard_normal((N, B, 32), dtype=np.float32)
+    mem0[:64] = 0.0                                       # the slots about to be overwritten start as ties
+    eng = EpisodicEngine(B, N, k=k, device=0)
+    assert eng.scan_geometry()["dynamic_chunk_tiles"] > 0
+    eng.load_memory(mem0)
+    qs = rng.standard_normal((steps, B, 32)).astype(np.float32) * 3.0     # far rows: they enter the farthest-k sets
+    al = (1.0 + 2.0 * rng.standard_normal((steps, B))).astype(np.float32)
+    q_dev, a_dev = torch.from_numpy(qs).cuda(), torch.from_numpy(al).cuda()
+    out = torch.empty(steps, B, device="cuda")
+    torch.cuda.synchronize()
+    for t in range(steps):                                # enqueue only
+        r_int, _ = eng.step(q_dev[t], a_dev[t])
+        out[t].copy_(r_int)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    orc = EpisodicOracle(B, N, k=k, use_c_scan=True)
+    orc.memory[...] = mem0
+    for t in range(steps):
+        want = orc.step(qs[t], al[t])
+        rel = np.abs(got[t] - want["reward"]) / np.abs(want["reward"])
+        assert rel.max() <= 1e-5, f"step {t}: reward rel err {rel.max():.2e}"
+    assert np.array_equal(eng.dump_memory(), orc.memory)
+    st = eng.get_state()
+    np.testing.assert_allclose(st["ed_mean"], orc.ed_rms.mean, rtol=1e-6)
+    assert st["exchange_timeouts"] == 0 and st["cursor"] == steps
+    eng.close()
