@@ -179,7 +179,8 @@ def run_gpu_arm(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     B, N = args.actors_per_gpu, args.capacity
     sh = ShardedEpisodicEngine(B * world, N, device=local_rank, k=K_NEIGHBORS,
-                               scan_variant=args.scan_variant, track_log_stats=True)
+                               scan_variant=args.scan_variant, track_log_stats=True,
+                               exchange=os.environ.get("NGU_BENCH_EXCHANGE", "auto"))   # experiments: "off" / "collective"
     eng = sh.engine
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     eng._memory.normal_(generator=g)                    # fully populated memory
@@ -264,7 +265,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                        "capacity": N, "k": K_NEIGHBORS, "mode": "reference", "parallelism": f"actor-shard x{world}",
                        "l2": f"working set {B * N * 128 / 1e6:.0f} MB per GPU vs 126 MB L2 (inputs larger than L2)"
                              if B * N * 128 > 2 * 126e6 else "working set fits L2: cache-resident, flagged",
-                       "exchange": "none" if world == 1 else (
+                       "exchange": "none" if world == 1 else "OFF (timing experiment: ranks independent)" if sh.exchange == "off" else (
                            "21-double rank sums + 5 log-only sums per step, NVLink peer stores fused into the finish kernel"
                            if sh.exchange == "p2p" else "21-double rank-sum all-reduce (torch.distributed) per step"),
                        "scan_geometry": geo},

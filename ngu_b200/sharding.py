@@ -60,6 +60,8 @@ class ShardedEpisodicEngine:
             exchange = "p2p" if (self.world > 1 and dist.get_backend(group) == "nccl"
                                  and hasattr(self.engine, "p2p_export")) else "collective"
         self.exchange = exchange if self.world > 1 else "none"
+        if self.exchange == "off":          # timing experiments only: ranks run independently (wrong global mean)
+            self.world = 1
         if self.exchange == "p2p":
             mine = self.engine.p2p_export(self.world)
             handles = [None] * self.world
