@@ -31,6 +31,7 @@ struct DevState {
     long long flush_seq;                // sequence number of on-demand log flush rounds
     long long cursor;
     long long exchange_timeouts;   // p2p exchange rounds that gave up waiting for a peer (must stay 0)
+    long long stash_open;          // 1: log_stash holds the rewards of a fused step not yet folded into the trackers
 };
 
 struct EpiConsts {
@@ -39,17 +40,18 @@ struct EpiConsts {
 };
 
 // ---------------------------------------------------------------------------
-// Code-size discipline: this kernel runs ONE CTA once per step, so its cost is
-// dominated by cold instruction fetches (its code is evicted from L2 by the 1 GB
-// scan between two launches).  Every IEEE-correct division / sqrt / reciprocal is
-// therefore a single out-of-line routine, loops are not unrolled, and the pairwise
-// summation is driven by a small host-built plan instead of recursion.
+// This kernel runs ONE CTA once per step; its cost is dependent-instruction latency, not
+// throughput and not instruction fetch (measured with %globaltimer stamps, tools/epilogue_phases.py:
+// a dry run of the whole post-wait body right before the real one does not make the real one
+// faster, and out-of-line IEEE helpers were ~0.25 us slower than inlined ones).  So: the chain
+// to the rewards is kept short (log-only work runs in other warps or in the next launch, see
+// log_absorb), loads are issued as one batch, and the helpers below are inlined.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float sqdiff_rn(float a, float b) { const float d = __fsub_rn(a, b); return __fmul_rn(d, d); }
-__device__ __noinline__ float f32_div(float a, float b) { return __fdiv_rn(a, b); }
-__device__ __noinline__ float f32_rcp(float a) { return __frcp_rn(a); }
-__device__ __noinline__ float f32_sqrt(float a) { return __fsqrt_rn(a); }
-__device__ __noinline__ double f64_div(double a, double b) { return a / b; }
+__device__ __forceinline__ float f32_div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float f32_rcp(float a) { return __frcp_rn(a); }
+__device__ __forceinline__ float f32_sqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ double f64_div(double a, double b) { return a / b; }
 
 // ---------------------------------------------------------------------------
 // numpy's float32 pairwise summation (x.sum(axis=0), mpi_util.py:11) over one
@@ -141,8 +143,10 @@ struct EpilogueParams {
     const float* rnd_targ;    // [B][128] RND target features
     float* alpha_out;         // [B] or null: the modulator computed by the RND phase
     P2PView p2p;              // used when phases & PH_EXCHANGE
+    float* log_stash;         // [2][B] r_epi, r_int of the last fused step (PH_LOGFUSE), see log_absorb
     unsigned int* host_flag;  // mapped host word or null: receives host_seq after the kernel's last write
     unsigned int host_seq;
+    unsigned long long* dbg_stamps;   // debug (NGU_EPI_DEBUG_EPILOGUE=1): %globaltimer at phase boundaries, thread 0
 };
 
 // Chan/Welford merge of (mean, var, count) with a batch (mpi_util.py:59-73), all f64.
@@ -179,6 +183,70 @@ __device__ __forceinline__ void apply_log_sums(DevState* st, double* s_scal, con
         rms_merge(&sc[0], &sc[1], &sc[2], m, v, n);
         for (int q = 0; q < 3; ++q) (&st->ed_count)[1 + 3 * which + q] = sc[q];
     }
+}
+
+// Fixed-order sum over the CTA of four f64 quantities: per-thread partials (thread t owns actors t,
+// t+THREADS, ...) -> xor-shuffle tree per warp -> xor-shuffle tree over the warp partials.
+// s_log[0..3] = the sums, s_log[4] = B.  All threads call it; ends with a barrier.
+template <int THREADS>
+__device__ __forceinline__ void log_tree_reduce(const double (&acc4)[4], double (*red)[THREADS / 32], double* s_log,
+                                                int B) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        double v = acc4[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            double v = threadIdx.x < THREADS / 32 ? red[q][threadIdx.x] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+            if (threadIdx.x == 0) s_log[q] = v;
+        }
+        if (threadIdx.x == 0) s_log[4] = static_cast<double>(B);
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// Deferred log-only trackers.  epi_novel_rms / intrinsic_novel_rms (episodic_novelty.py:82,
+// intrinsic_novelty.py:32) are never read by the hot path, yet their batch sums and Chan merges
+// (f64 shuffles and divisions, ~2 us of dependent latency) used to sit at the end of every
+// step's critical path.  A PH_LOGFUSE launch now only stashes its per-actor rewards and raises
+// DevState::stash_open; the NEXT fused launch folds the stash into the trackers before its
+// griddepcontrol.wait, i.e. while its scan is still streaming (the CTA is resident 15-60 us
+// early).  That is safe because a fused epilogue always follows its scan kernel, and the scan
+// signals launch_dependents only AFTER its own griddepcontrol.wait: when this CTA starts, the
+// previous epilogue (and everything else earlier in the stream) has completed.  Everything is
+// device state, so a captured CUDA graph replays correctly.  ngu_epi_get_state and
+// ngu_epi_log_flush run the same routine from log_absorb_kernel.  The sums are formed in the
+// same fixed order as before (log_tree_reduce): the trackers hold the same bits, one launch later.
+// All threads of the CTA call it.
+// ---------------------------------------------------------------------------
+template <int THREADS>
+__device__ __noinline__ void log_absorb(DevState* st, const float* stash, int B, bool to_pending,
+                                        double (*red)[THREADS / 32], double* s_log) {
+    double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+    for (int b = threadIdx.x; b < B; b += THREADS) {
+        const float r = __ldcg(stash + b), ri = __ldcg(stash + B + b);
+        acc4[0] += r; acc4[1] += static_cast<double>(r) * r;
+        acc4[2] += ri; acc4[3] += static_cast<double>(ri) * ri;
+    }
+    log_tree_reduce<THREADS>(acc4, red, s_log, B);
+    if (to_pending) {            // p2p mode: this shard's sums wait for the next exchange round
+        if (threadIdx.x < 5) st->pending_log[threadIdx.x] = s_log[threadIdx.x];
+    } else if (threadIdx.x < 2) {
+        double sc[7];                                       // laid out like the staged scalar block
+        for (int q = 0; q < 3; ++q) sc[1 + 3 * threadIdx.x + q] = __ldcg(&st->ed_count + 1 + 3 * threadIdx.x + q);
+        apply_log_sums(st, sc, s_log, threadIdx.x);
+    }
+    if (threadIdx.x == 32) st->stash_open = 0;
+    __syncthreads();
 }
 
 // torch.max(x, 0) semantics (NaN propagates), episodic_novelty.py:60-65
@@ -219,6 +287,8 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
     DevState* st = p.state;
     const bool finish = (p.phases & PH_FINISH) != 0, append = (p.phases & PH_APPEND) != 0;
 
+#define EPI_STAMP(i) do { if (p.dbg_stamps && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg_stamps[i] = t_; } } while (0)
+    EPI_STAMP(8);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // next step's scan may start its prologue
 
     // While the scan is still streaming: pull this kernel's small inputs into L2 (the scan's TMA
@@ -265,11 +335,32 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
         for (int i = threadIdx.x; i < B * 8; i += THREADS) s_q[i] = __ldcg(reinterpret_cast<const float4*>(p.q) + i);
     }
 
+    // The previous fused step's reward stash -> log-only trackers, while the scan drains (see log_absorb).
+    const bool logfuse = finish && (p.phases & PH_LOGFUSE) != 0;
+    if (logfuse) {
+        if (threadIdx.x == 0) s_cursor = __ldcg(&st->stash_open);      // s_cursor: scratch until the load phase
+        __syncthreads();
+        const bool open = s_cursor != 0;
+        __syncthreads();
+        if (open) log_absorb<THREADS>(st, p.log_stash, B, (p.phases & PH_EXCHANGE) != 0, red, s_log);
+    }
+
+    EPI_STAMP(9);
     asm volatile("griddepcontrol.wait;" ::: "memory");               // scan kernel complete, its writes visible
+    EPI_STAMP(0);
 
     // ---- one batch of independent loads: everything the phases below need goes on chip ----
+    // dist goes global -> shared as 16-byte cp.async (L2 only): every chunk is in flight at once instead of
+    // one L2 round trip per loop iteration
+    {
+        const int n16 = (B * k) >> 2;
+        const unsigned s_base = static_cast<unsigned>(__cvta_generic_to_shared(s_dist));
 #pragma unroll 1
-    for (int i = threadIdx.x; i < B * k; i += THREADS) s_dist[i] = __ldcg(p.dist + i);
+        for (int i = threadIdx.x; i < n16; i += THREADS)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_base + 16u * i), "l"(p.dist + 4 * i) : "memory");
+        const int t = (n16 << 2) + threadIdx.x;
+        if (t < B * k) s_dist[t] = __ldcg(p.dist + t);
+    }
     if (finish) {
         if (p.sums_in && threadIdx.x < 2 * k + 1) s_sums[threadIdx.x] = __ldcg(p.sums_in + threadIdx.x);
         if (threadIdx.x < k) {
@@ -282,7 +373,9 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
         if (threadIdx.x == 64) s_cursor = __ldcg(&st->cursor);
     }
     if (threadIdx.x >= 96 && threadIdx.x < 96 + p.plan_len && threadIdx.x < 160) s_plan[threadIdx.x - 96] = __ldcg(p.plan + (threadIdx.x - 96));
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
+    EPI_STAMP(1);
 
     if (rnd) {
         // ll_rms.update(err) with use_mpi=False (mpi_util.py:51-52: np.mean / np.std over the local batch,
@@ -356,6 +449,7 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
         if (threadIdx.x < 2 * k + 1) p.rank_sums[threadIdx.x] = s_sums[threadIdx.x];
     }
 
+    EPI_STAMP(2);
     const bool exchange = (p.phases & PH_EXCHANGE) != 0;
     if (exchange) {
         // ONE exchange per step: this step's rank sums (mpi_util.py:17) and, piggybacked, the log-only
@@ -371,47 +465,63 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
         __syncthreads();
     }
 
+    EPI_STAMP(3);
     if (finish) {
-        if (threadIdx.x < k) {
-            const int j = threadIdx.x;
+        // RunningMeanStd.update_from_moments (mpi_util.py:59-73).  Only the MEAN feeds the rewards
+        // (episodic_novelty.py:58), so warp 0 runs the short chain to it while warp 1 runs the longer
+        // variance chain (log-only) side by side.
+        if ((threadIdx.x & 31) < k && threadIdx.x < 64) {
+            const int j = threadIdx.x & 31;
             const double cnt = s_sums[2 * k];
             const float cnt32 = static_cast<float>(cnt);
             // mpi_mean: globalsum[:n] / globalsum[n] in float32 (mpi_util.py:18)
             const float b_mean = f32_div(static_cast<float>(s_sums[j]), cnt32);
-            // mpi_moments' second pass (mpi_util.py:25-28) from the f64 sum of squares:
-            // E[(x-m)^2] = E[x^2] - 2 m E[x] + m^2 with m the f32 batch mean.
-            const double ex = f64_div(s_sums[j], cnt), ex2 = f64_div(s_sums[k + j], cnt), bm = static_cast<double>(b_mean);
-            const float msd = static_cast<float>(fmax(ex2 - 2.0 * bm * ex + bm * bm, 0.0));
-            const float b_std = f32_sqrt(msd);
-            const float b_var = __fmul_rn(b_std, b_std);                      // np.square(batch_std), :56
-            const double m_b = static_cast<double>(__fmul_rn(b_var, cnt32)); // batch_var * batch_count (f32), :65
+            const double bm = static_cast<double>(b_mean);
             const double count = s_scal[0];
             const double n_b = static_cast<double>(cnt32);
             const double delta = bm - s_mean[j];
             const double totc = count + n_b;
-            const double new_mean = s_mean[j] + f64_div(delta * n_b, totc);
-            const double m2 = s_var[j] * count + m_b + f64_div(delta * delta * count * n_b, totc);
-            st->ed_mean[j] = new_mean;
-            st->ed_var[j] = f64_div(m2, totc);
-            mean32[j] = static_cast<float>(new_mean);   // ptu.to_tensor(...).float(), pytorch_util.py:20
+            if (threadIdx.x < 32) {
+                const double new_mean = s_mean[j] + f64_div(delta * n_b, totc);
+                st->ed_mean[j] = new_mean;
+                mean32[j] = static_cast<float>(new_mean);   // ptu.to_tensor(...).float(), pytorch_util.py:20
+            } else {
+                // mpi_moments' second pass (mpi_util.py:25-28) from the f64 sum of squares:
+                // E[(x-m)^2] = E[x^2] - 2 m E[x] + m^2 with m the f32 batch mean.
+                const double ex = f64_div(s_sums[j], cnt), ex2 = f64_div(s_sums[k + j], cnt);
+                const float msd = static_cast<float>(fmax(ex2 - 2.0 * bm * ex + bm * bm, 0.0));
+                const float b_std = f32_sqrt(msd);
+                const float b_var = __fmul_rn(b_std, b_std);                      // np.square(batch_std), :56
+                const double m_b = static_cast<double>(__fmul_rn(b_var, cnt32)); // batch_var * batch_count (f32), :65
+                const double m2 = s_var[j] * count + m_b + f64_div(delta * delta * count * n_b, totc);
+                st->ed_var[j] = f64_div(m2, totc);
+            }
         }
-        if (threadIdx.x == 32) {
+        if (threadIdx.x == 64) {
             st->ed_count = s_scal[0] + static_cast<double>(static_cast<float>(s_sums[2 * k]));
             st->steps = st_steps_plus_one(s_scal[7]);
         }
         __syncthreads();
+        EPI_STAMP(4);
 
+        // (i) one thread per (actor, neighbour): the IEEE division and reciprocal each hide a branch to a
+        // slow path, so ptxas will not interleave them - k of them in one thread are k serial chains
+        const int j_step = THREADS % k;
+        int j = threadIdx.x % k;
+#pragma unroll 1
+        for (int e = threadIdx.x; e < B * k; e += THREADS, j = j + j_step >= k ? j + j_step - k : j + j_step) {
+            const float nd = __fdiv_rn(s_dist[e], mean32[j]);                   // :58
+            const float cl = relu_nanprop(__fsub_rn(nd, c.cluster));            // :60-65
+            s_dist[e] = __fmul_rn(__frcp_rn(__fadd_rn(cl, c.eps)), c.eps);      // :67-68 (reciprocal()*eps), in place
+        }
+        __syncthreads();
+        // (ii) one thread per actor
         double acc4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
         for (int b = threadIdx.x; b < B; b += THREADS) {
-            float acc = 0.0f;
-#pragma unroll 5
-            for (int j = 0; j < k; ++j) {   // iterations are independent up to the final add: unrolled for ILP
-                const float nd = __fdiv_rn(s_dist[b * k + j], mean32[j]);           // :58
-                const float cl = relu_nanprop(__fsub_rn(nd, c.cluster));            // :60-65
-                const float kv = __fmul_rn(__frcp_rn(__fadd_rn(cl, c.eps)), c.eps); // :67-68 (reciprocal()*eps)
-                acc = (j == 0) ? kv : __fadd_rn(acc, kv);                           // :71 sum(dim=0)
-            }
+            float acc = s_dist[b * k];
+#pragma unroll 8
+            for (int jj = 1; jj < k; ++jj) acc = __fadd_rn(acc, s_dist[b * k + jj]);   // :71 sum(dim=0), sequential; loads hoisted
             const float sim = __fadd_rn(f32_sqrt(acc), c.pseudo);                   // :71-72
             float r = f32_rcp(sim);                                                 // :75
             if (sim > c.s_max) r = 0.0f;                                            // :76-78
@@ -421,43 +531,23 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
             const float ri = __fmul_rn(r, a);                                       // :31
             if (p.r_epi) p.r_epi[b] = r;
             p.r_int[b] = ri;
-            acc4[0] += r; acc4[1] += static_cast<double>(r) * r;
-            acc4[2] += ri; acc4[3] += static_cast<double>(ri) * ri;
+            if (logfuse) {       // log-only statistics: stashed, absorbed by the next launch (log_absorb)
+                p.log_stash[b] = r;
+                p.log_stash[B + b] = ri;
+            } else if (p.log_sums) {
+                acc4[0] += r; acc4[1] += static_cast<double>(r) * r;
+                acc4[2] += ri; acc4[3] += static_cast<double>(ri) * ri;
+            }
         }
-
-        // log-only batch sums (epi_novel_rms / intrinsic_novel_rms), fixed-order tree
-        if (p.log_sums || (p.phases & PH_LOGFUSE)) {
-#pragma unroll 1
-            for (int q = 0; q < 4; ++q) {
-                double v = acc4[q];
-#pragma unroll 1
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-                if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v;
-            }
-            __syncthreads();
-            if (threadIdx.x < 32) {
-                // lanes 0..15 hold one warp partial each; 4 quantities reduced by shuffles
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    double v = threadIdx.x < THREADS / 32 ? red[q][threadIdx.x] : 0.0;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-                    if (threadIdx.x == 0) s_log[q] = v;
-                }
-                if (threadIdx.x == 0) s_log[4] = static_cast<double>(B);
-            }
-            __syncthreads();
-            if (p.log_sums && threadIdx.x < 5) p.log_sums[threadIdx.x] = s_log[threadIdx.x];
-            if (p.phases & PH_LOGFUSE) {
-                if (exchange) {          // p2p mode: keep them for the next step's exchange
-                    if (threadIdx.x < 5) st->pending_log[threadIdx.x] = s_log[threadIdx.x];
-                } else if (threadIdx.x < 2) {
-                    apply_log_sums(st, s_scal, s_log, threadIdx.x);
-                }
-            }
+        if (logfuse && threadIdx.x == 96) st->stash_open = 1;
+        EPI_STAMP(5);
+        if (p.log_sums && !logfuse) {   // split sequence: the caller reduces the log-only sums over the shards itself
+            log_tree_reduce<THREADS>(acc4, red, s_log, B);
+            if (threadIdx.x < 5) p.log_sums[threadIdx.x] = s_log[threadIdx.x];
         }
     }
 
+    EPI_STAMP(6);
     if (append) {
         const long long cur = s_cursor;
         const float4* q4 = reinterpret_cast<const float4*>(p.q);
@@ -470,6 +560,7 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
         if (threadIdx.x == 64) st->cursor = (cur + 1) % c.capacity;
     }
 
+    EPI_STAMP(7);
     if (p.host_flag) {   // ngu_epi_step_host: tell the spinning host that every write of the step has been issued
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -481,16 +572,31 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
 
 // On-demand flush of the deferred log-only sums (p2p mode): one exchange round of 5 doubles,
 // then the tracker update; all ranks must launch it together.
-__global__ void __launch_bounds__(128) log_flush_kernel(DevState* st, P2PView v) {
+constexpr int kLogThreads = 512;   // = the epilogue's CTA size: log_tree_reduce must add in the same order
+
+// Stand-alone absorb (ngu_epi_get_state, ngu_epi_log_flush outside p2p mode).
+__global__ void __launch_bounds__(kLogThreads) log_absorb_kernel(DevState* st, const float* stash, int B, int to_pending) {
+    __shared__ double red[4][kLogThreads / 32];
+    __shared__ double s_log[8];
+    if (__ldcg(&st->stash_open) == 0) return;              // CTA-uniform
+    log_absorb<kLogThreads>(st, stash, B, to_pending != 0, red, s_log);
+}
+
+__global__ void __launch_bounds__(kLogThreads) log_flush_kernel(DevState* st, P2PView v, const float* stash, int B) {
     __shared__ double s_scal[16];
     __shared__ double s_vals[8];
     __shared__ double s_recv[kMaxWorld * 8];
+    __shared__ double red[4][kLogThreads / 32];
+    __shared__ double s_log[8];
+    if (__ldcg(&st->stash_open) != 0)                      // CTA-uniform
+        log_absorb<kLogThreads>(st, stash, B, true, red, s_log);
+    __syncthreads();
     if (threadIdx.x < 16) s_scal[threadIdx.x] = __ldcg(&st->ed_count + threadIdx.x);
     __syncthreads();
     if (threadIdx.x < 5) s_vals[threadIdx.x] = s_scal[11 + threadIdx.x];
     __syncthreads();
     const unsigned long long seq = static_cast<unsigned long long>(st->flush_seq);
-    if (!p2p_allreduce<128>(v, s_vals, 5, kFlushElem, seq, s_recv) && threadIdx.x == 0)
+    if (!p2p_allreduce<kLogThreads>(v, s_vals, 5, kFlushElem, seq, s_recv) && threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(&st->exchange_timeouts), 1ull);
     if (threadIdx.x < 2) apply_log_sums(st, s_scal, s_vals, threadIdx.x);
     if (threadIdx.x < 5) st->pending_log[threadIdx.x] = 0.0;

@@ -96,6 +96,7 @@ struct ngu_epi {
     float* dist = nullptr;           // [B][k]
     double* rank_sums = nullptr;     // [2k+1]
     double* log_sums = nullptr;      // [5]
+    float* log_stash = nullptr;      // [2][B] rewards of the last fused step, not yet in the log-only trackers (log_absorb)
     u64* actor_state = nullptr;              // [B][2] per actor {published floor, arrived tiles << 32 | reserved candidates}
     unsigned int* sched_ctr = nullptr;       // [8] dynamic chunk counter, finished-warp counter, launch epoch, merge-job counter, leftovers
     int32_t* leftover = nullptr;             // [B] merge jobs given up by their first taker (scan_topk.cuh: merge_job)
@@ -117,6 +118,7 @@ struct ngu_epi {
     unsigned long long* timeline = nullptr;   // NGU_EPI_DEBUG_TIMELINE=1: per-warp timestamps of the last scan
     int debug_phase_mask = ~0;       // NGU_EPI_DEBUG_PHASES: experiments only (tools/sweep.py)
     int debug_scan = 0;              // NGU_EPI_DEBUG_SCAN: experiments only (ScanParams::debug)
+    unsigned long long* epi_stamps = nullptr;   // NGU_EPI_DEBUG_EPILOGUE=1: phase stamps of the last epilogue launch
     // staging for the *_host entry points
     cudaStream_t own_stream = nullptr;
     float* q_stage_dev = nullptr;    // [B][32] followed by alpha [B]: one H2D copy per step
@@ -328,6 +330,12 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
         }
     }
     if (const char* e = getenv("NGU_EPI_DEBUG_PHASES")) h->debug_phase_mask = atoi(e);
+    if (const char* e = getenv("NGU_EPI_DEBUG_EPILOGUE")) {
+        if (atoi(e) != 0) {
+            CREATE_TRY(cudaMalloc(&h->epi_stamps, 16 * sizeof(unsigned long long)));
+            CREATE_TRY(cudaMemset(h->epi_stamps, 0, 16 * sizeof(unsigned long long)));
+        }
+    }
     if (const char* e = getenv("NGU_EPI_DEBUG_SCAN")) h->debug_scan = atoi(e);
     apply_sched_env(h);
     plan_geometry(h);
@@ -351,6 +359,7 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
     CREATE_TRY(cudaMalloc(&h->dist, static_cast<size_t>(B) * k * sizeof(float)));
     CREATE_TRY(cudaMalloc(&h->rank_sums, NGU_EPI_RANK_SUMS(NGU_EPI_MAX_K) * sizeof(double)));
     CREATE_TRY(cudaMalloc(&h->log_sums, 8 * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->log_stash, 2 * static_cast<size_t>(cfg->n_actors) * sizeof(float)));
     CREATE_TRY(cudaMalloc(&h->actor_state, static_cast<size_t>(B) * 2 * sizeof(u64)));
     CREATE_TRY(cudaMemset(h->actor_state, 0, static_cast<size_t>(B) * 2 * sizeof(u64)));
     CREATE_TRY(cudaMalloc(&h->leftover, static_cast<size_t>(B) * sizeof(int32_t)));
@@ -421,7 +430,7 @@ void ngu_epi_destroy(ngu_epi* h) {
     cudaFree(h->inbox);
     if (h->owns_memory) cudaFree(h->memory);
     cudaFree(h->cand); cudaFree(h->topk_d2); cudaFree(h->topk_idx); cudaFree(h->dist);
-    cudaFree(h->rank_sums); cudaFree(h->log_sums); cudaFree(h->state); cudaFree(h->actor_state); cudaFree(h->sched_ctr); cudaFree(h->leftover); cudaFree(h->plan_dev); cudaFree(h->timeline);
+    cudaFree(h->rank_sums); cudaFree(h->log_sums); cudaFree(h->log_stash); cudaFree(h->state); cudaFree(h->actor_state); cudaFree(h->sched_ctr); cudaFree(h->leftover); cudaFree(h->plan_dev); cudaFree(h->timeline); cudaFree(h->epi_stamps);
     cudaFree(h->q_stage_dev); cudaFree(h->done_stage_dev);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->r_mapped) cudaFreeHost(h->r_mapped);
@@ -486,6 +495,7 @@ static int launch_epilogue(ngu_epi* h, int phases, const double* sums_in, const 
                            const RndArgs* rnd = nullptr, const HostFlag* hf = nullptr) {
     EpilogueParams ep{};
     if (hf) { ep.host_flag = hf->flag; ep.host_seq = hf->seq; }
+    ep.dbg_stamps = h->epi_stamps;
     if (rnd) { ep.rnd_pred = rnd->pred; ep.rnd_targ = rnd->targ; ep.alpha_out = rnd->alpha_out; }
     ep.dist = h->dist; ep.rank_sums = h->rank_sums; ep.sums_in = sums_in; ep.alpha = alpha;
     ep.r_int = r_int; ep.r_epi = r_epi; ep.log_sums = log_sums; ep.q = q; ep.memory = h->memory;
@@ -495,6 +505,7 @@ static int launch_epilogue(ngu_epi* h, int phases, const double* sums_in, const 
         ep.p2p = h->p2p;
     }
     ep.plan = h->plan_dev; ep.plan_len = h->plan_len;
+    ep.log_stash = h->log_stash;
     // dynamic smem: [dist B*k][alpha B][q B*32] when it all fits, else without q
     ep.stage_q = epilogue_smem_bytes(h->cfg.n_actors, h->cfg.k, true) <= kEpilogueStageBytes ? 1 : 0;
     const size_t dyn = epilogue_smem_bytes(h->cfg.n_actors, h->cfg.k, ep.stage_q != 0);
@@ -695,6 +706,10 @@ int ngu_epi_get_state(ngu_epi* h, ngu_epi_state* out) {
     if (rc) return rc;
     DevState d;
     CU_TRY(h, cudaDeviceSynchronize());
+    // bring the log-only trackers up to date (p2p mode: into pending_log; see ngu_epi_log_flush)
+    log_absorb_kernel<<<1, kLogThreads>>>(h->state, h->log_stash, h->cfg.n_actors, h->p2p_connected ? 1 : 0);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaDeviceSynchronize());
     CU_TRY(h, cudaMemcpy(&d, h->state, sizeof d, cudaMemcpyDeviceToHost));
     std::memcpy(out->ed_mean, d.ed_mean, sizeof d.ed_mean);
     std::memcpy(out->ed_var, d.ed_var, sizeof d.ed_var);
@@ -800,10 +815,14 @@ int ngu_epi_p2p_connect(ngu_epi* h, int32_t rank, int32_t world, const void* ipc
 
 int ngu_epi_log_flush(ngu_epi* h, void* stream) {
     if (!h) return fail(h, NGU_EINVAL, "null argument");
-    if (!h->p2p_connected) return NGU_OK;     // nothing is deferred outside p2p mode
     int rc = bind_device(h);
     if (rc) return rc;
-    log_flush_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->state, h->p2p);
+    if (!h->p2p_connected) {                  // only the reward stash of the last fused step is outstanding
+        log_absorb_kernel<<<1, kLogThreads, 0, static_cast<cudaStream_t>(stream)>>>(h->state, h->log_stash, h->cfg.n_actors, 0);
+    } else {
+        log_flush_kernel<<<1, kLogThreads, 0, static_cast<cudaStream_t>(stream)>>>(h->state, h->p2p, h->log_stash,
+                                                                                  h->cfg.n_actors);
+    }
     CU_TRY(h, cudaGetLastError());
     h->launches += 1;
     return NGU_OK;
@@ -811,6 +830,14 @@ int ngu_epi_log_flush(ngu_epi* h, void* stream) {
 
 int ngu_epi_debug_timeline(ngu_epi* h, uint64_t* out_host, int32_t max_warps) {
     if (!h || !out_host) return fail(h, NGU_EINVAL, "null argument");
+    if (max_warps < 0 && max_warps >= -16) {   // the epilogue's phase stamps instead (NGU_EPI_DEBUG_EPILOGUE=1)
+        const int n = -max_warps;
+        if (!h->epi_stamps) return fail(h, NGU_ESTATE, "create the handle with NGU_EPI_DEBUG_EPILOGUE=1");
+        if (cudaDeviceSynchronize() != cudaSuccess ||
+            cudaMemcpy(out_host, h->epi_stamps, n * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return fail(h, NGU_ECUDA, "copying the epilogue stamps failed");
+        return n;
+    }
     if (!h->timeline) return fail(h, NGU_ESTATE, "create the handle with NGU_EPI_DEBUG_TIMELINE=1");
     int rc = bind_device(h);
     if (rc) return rc;

@@ -541,7 +541,6 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
     const uint32_t aux0 = desc0 + WARPS * STAGES * 8;     // 16-byte aligned: everything before it is a multiple of 16
     const uint32_t my_aux = aux0 + warp * STAGES * Cfg::kAuxBytes;
 
-    pdl_launch_dependents();   // the epilogue kernel may become resident now; it waits on us
     const int gw = blockIdx.x * WARPS + warp;
     const int n_warps = gridDim.x * WARPS;
     const unsigned long long tl0 = p.timeline ? globaltimer_ns() : 0ull;
@@ -577,6 +576,11 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
     }
     __syncwarp();
     pdl_wait();   // predecessor (previous step's epilogue: append, readers of dist/topk) is complete
+    // Only now may this step's epilogue become resident (it waits on us): signalled AFTER the wait, so that an
+    // epilogue CTA never runs concurrently with the previous epilogue - its pre-wait section reads state the
+    // previous one writes (epilogue.cuh, log_absorb).  Costs nothing: it could not become resident before one of
+    // our CTAs exits (shared memory) or, on small grids, has tens of microseconds of streaming left to do so.
+    pdl_launch_dependents();
 
     const uint64_t policy = l2_evict_first_policy();
     const uint32_t tag = __ldcg(p.sched_ctr + 2);   // launch epoch (first needed at the first flush)

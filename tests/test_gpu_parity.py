@@ -203,3 +203,44 @@ def test_dynamic_schedule_vs_oracle(cuda_device, monkeypatch, sched, epoch, k, m
     assert eng.get_state()["exchange_timeouts"] == 0, "a merge gave up waiting for a candidate"
     assert np.array_equal(eng.dump_memory(), orc.memory)
     eng.close()
+
+
+def _same_state(a, b):
+    assert a.keys() == b.keys()
+    for key in a:
+        assert np.array_equal(np.asarray(a[key]), np.asarray(b[key])), key
+
+
+@pytest.mark.parametrize("B,N", [(7, 600), (256, 2000), (700, 300)])
+def test_deferred_log_trackers(cuda_device, B, N):
+    """epi_novel_rms / intrinsic_novel_rms (episodic_novelty.py:82, intrinsic_novelty.py:32) are folded into
+    the device trackers one launch late, by the next step's epilogue while its scan drains, or by
+    ngu_epi_get_state.  Both routes must give the same bits, and the trackers must follow the
+    reference's RunningMeanStd fed with the rewards the steps returned."""
+    import torch
+    from ngu_b200.engine import EpisodicEngine
+    from oracle.episodic_oracle import RunningMeanStdOracle
+    rng = np.random.default_rng(B + N)
+    mem0 = rng.standard_normal((N, B, 32), dtype=np.float32)
+    lazy = EpisodicEngine(B, N, device=0); lazy.load_memory(mem0)      # absorbs inside the epilogue kernel
+    eager = EpisodicEngine(B, N, device=0); eager.load_memory(mem0)    # get_state after every step
+    epi, intr = RunningMeanStdOracle(1e-4), RunningMeanStdOracle(1e-4)
+    T = 25
+    for t in range(T):
+        q = torch.from_numpy(rng.standard_normal((B, 32), dtype=np.float32)).cuda()
+        alpha = torch.from_numpy((1.0 + 2.0 * rng.standard_normal(B)).astype(np.float32)).cuda()
+        r_int, r_epi = lazy.step(q, alpha)
+        r2, _ = eager.step(q, alpha)
+        assert torch.equal(r_int, r2)
+        epi.update(r_epi.cpu().numpy()); intr.update(r_int.cpu().numpy())
+        se = eager.get_state()
+        if t % 6 == 5:                       # a state read in the middle of the lazy run must not double count
+            _same_state(lazy.get_state(), se)
+    sl = lazy.get_state()
+    _same_state(sl, eager.get_state())
+    assert sl["epi_count"] == epi.count and sl["intr_count"] == intr.count
+    np.testing.assert_allclose(sl["epi_mean"], epi.mean, rtol=1e-6)
+    np.testing.assert_allclose(sl["intr_mean"], intr.mean, rtol=1e-6)
+    np.testing.assert_allclose(sl["epi_var"], epi.var, rtol=1e-3)
+    np.testing.assert_allclose(sl["intr_var"], intr.var, rtol=1e-3)
+    lazy.close(); eager.close()
