@@ -644,6 +644,24 @@ __global__ void __launch_bounds__(256) reset_kernel(float* __restrict__ mem, con
     }
 }
 
+// ---------------------------------------------------------------------------
+// ngu_epi_step_host: the step's inputs (controllable states + modulators, B*132 bytes in pinned, mapped
+// host memory) are pulled over PCIe by this kernel instead of by a copy-engine transfer.  A kernel can be
+// chained with programmatic dependent launch, a memcpy cannot: the scan's CTAs become resident and issue
+// their L2 prefetches while these loads are in flight, instead of being launched after the copy has
+// completed.  One 16-byte load per thread, all in flight at once.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stage_inputs_kernel(float4* __restrict__ dst, const float4* src_host, int n16) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n16) {
+        float4 v;
+        asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src_host + i) : "memory");
+        dst[i] = v;
+    }
+}
+
 // Layout converters for load/dump in the reference's slot-major [N][B][32] order.
 __global__ void transpose_rows_kernel(float4* __restrict__ dst, const float4* __restrict__ src, int outer,
                                       int inner) {

@@ -124,7 +124,10 @@ struct ngu_epi {
     float* q_stage_dev = nullptr;    // [B][32] followed by alpha [B]: one H2D copy per step
     float* a_stage_dev = nullptr;    // = q_stage_dev + B*32
     uint8_t* done_stage_dev = nullptr;
-    float* pinned = nullptr;         // host: [B*32 q][B alpha] floats + B done bytes
+    float* pinned = nullptr;         // host, mapped: [B*32 q][B alpha] floats + B done bytes
+    float* pinned_dev = nullptr;     // device alias of pinned (stage_inputs_kernel reads it over PCIe)
+    bool stage_by_kernel = false;    // ngu_epi_step_host pulls its inputs with stage_inputs_kernel (large shapes) or the
+                                     // copy engine (small ones); NGU_EPI_HOST_STAGE=copy|kernel forces one (tools/host_path_ab.py)
     float* r_mapped = nullptr;       // host, mapped: [2][B] rewards written by the epilogue over PCIe (zero-copy)
     float* r_mapped_dev = nullptr;   // device alias of r_mapped
     // completion of the *_host step: a mapped word the epilogue stores after its last write and the host
@@ -382,10 +385,15 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
         CREATE_TRY(cudaMemcpy(h->plan_dev, plan.data(), plan.size() * sizeof(int2), cudaMemcpyHostToDevice));
     }
     CREATE_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    CREATE_TRY(cudaMalloc(&h->q_stage_dev, static_cast<size_t>(B) * 33 * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&h->q_stage_dev, static_cast<size_t>(B) * 33 * sizeof(float) + 16));
     h->a_stage_dev = h->q_stage_dev + static_cast<size_t>(B) * 32;
     CREATE_TRY(cudaMalloc(&h->done_stage_dev, static_cast<size_t>(B)));
-    CREATE_TRY(cudaMallocHost(&h->pinned, static_cast<size_t>(B) * 33 * sizeof(float) + B));
+    CREATE_TRY(cudaHostAlloc(&h->pinned, static_cast<size_t>(B) * 33 * sizeof(float) + B + 16, cudaHostAllocMapped));
+    CREATE_TRY(cudaHostGetDevicePointer(&h->pinned_dev, h->pinned, 0));
+    // measured (tools/host_path_ab.py): the PDL-chained kernel wins 1.5 us per step at 256 x 30k and 3.7 us at
+    // 1024 x 30k, the copy engine wins 1.2-1.8 us on steps of a few tens of microseconds
+    h->stage_by_kernel = static_cast<double>(B) * cfg->capacity * 128.0 >= 512e6;
+    if (const char* e = getenv("NGU_EPI_HOST_STAGE")) h->stage_by_kernel = std::strcmp(e, "copy") != 0;
     CREATE_TRY(cudaHostAlloc(&h->r_mapped, static_cast<size_t>(B) * 2 * sizeof(float), cudaHostAllocMapped));
     CREATE_TRY(cudaHostGetDevicePointer(&h->r_mapped_dev, h->r_mapped, 0));
     CREATE_TRY(cudaHostAlloc(&h->flag_mapped, 64, cudaHostAllocMapped));
@@ -647,8 +655,17 @@ int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host, 
     std::memcpy(h->pinned, q_host, B * 32 * sizeof(float));
     if (alpha_host) std::memcpy(h->pinned + B * 32, alpha_host, B * sizeof(float));
     if (prof) t1 = clk::now();
-    CU_TRY(h, cudaMemcpyAsync(h->q_stage_dev, h->pinned, B * (alpha_host ? 33 : 32) * sizeof(float),
-                              cudaMemcpyHostToDevice, s));
+    if (h->stage_by_kernel && h->use_pdl) {
+        // whole 16-byte pieces: both buffers are padded, a few floats past the modulators ride along
+        const int n16 = static_cast<int>((B * (alpha_host ? 33 : 32) + 3) / 4);
+        stage_inputs_kernel<<<(n16 + 255) / 256, 256, 0, s>>>(reinterpret_cast<float4*>(h->q_stage_dev),
+                                                              reinterpret_cast<const float4*>(h->pinned_dev), n16);
+        CU_TRY(h, cudaGetLastError());
+        h->launches += 1;
+    } else {
+        CU_TRY(h, cudaMemcpyAsync(h->q_stage_dev, h->pinned, B * (alpha_host ? 33 : 32) * sizeof(float),
+                                  cudaMemcpyHostToDevice, s));
+    }
     const float* q_dev = h->q_stage_dev;
     // the rewards come back zero-copy: the epilogue writes them straight into mapped host memory
     rc = step_impl(h, q_dev, alpha_host ? q_dev + B * 32 : nullptr, h->r_mapped_dev, h->r_mapped_dev + B, s,

@@ -244,3 +244,30 @@ def test_deferred_log_trackers(cuda_device, B, N):
     np.testing.assert_allclose(sl["epi_var"], epi.var, rtol=1e-3)
     np.testing.assert_allclose(sl["intr_var"], intr.var, rtol=1e-3)
     lazy.close(); eager.close()
+
+
+@pytest.mark.parametrize("stage", ["kernel", "copy"])
+@pytest.mark.parametrize("B", [1, 3, 64])
+def test_host_step_input_staging(cuda_device, monkeypatch, stage, B):
+    """ngu_epi_step_host moves the step's inputs host -> device either with a PDL-chained kernel that reads
+    the pinned buffer over PCIe (large shapes by default) or with the copy engine; both against the oracle,
+    including actor counts whose modulator block is not a whole number of 16-byte pieces."""
+    from ngu_b200.engine import EpisodicEngine
+    from oracle.episodic_oracle import EpisodicOracle
+    monkeypatch.setenv("NGU_EPI_HOST_STAGE", stage)
+    N = 1200
+    rng = np.random.default_rng(17 * B)
+    mem0 = rng.standard_normal((N, B, 32), dtype=np.float32)
+    orc = EpisodicOracle(B, N); orc.memory[...] = mem0
+    eng = EpisodicEngine(B, N, device=0); eng.load_memory(mem0)
+    for t in range(5):
+        q = rng.standard_normal((B, 32), dtype=np.float32)
+        alpha = (1.0 + 2.0 * rng.standard_normal(B)).astype(np.float32) if t % 2 == 0 else None
+        ref = orc.step(q, alpha)
+        r_int, _ = eng.step_host(q, alpha)
+        d2, idx = eng.topk()
+        assert np.array_equal(idx.T, ref["idx"])
+        assert np.array_equal(d2.T.view(np.uint32), ref["d2"].view(np.uint32))
+        assert _rel(r_int.astype(np.float64), ref["reward"]).max() <= REL_TOL
+    assert np.array_equal(eng.dump_memory(), orc.memory)
+    eng.close()

@@ -1,11 +1,11 @@
-"""Scratch: A/B of the host-buffer step (ngu_epi_step_host): zero-copy + mapped flag vs staged H2D + stream sync."""
+"""Scratch: A/B of the host-buffer step (ngu_epi_step_host): inputs staged by the copy engine vs pulled by a PDL-chained kernel."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from ngu_b200.engine import EpisodicEngine
 
 def run(B, N, mode, steps=300):
-    os.environ["NGU_EPI_HOST_PATH"] = mode
+    os.environ["NGU_EPI_HOST_STAGE"] = mode
     eng = EpisodicEngine(B, N, device=0)
     eng._memory.normal_()
     rng = np.random.default_rng(0)
@@ -23,5 +23,5 @@ def run(B, N, mode, steps=300):
 
 if __name__ == "__main__":
     for (B, N) in [(256, 30000), (64, 5000), (1, 30000), (32, 30000), (1024, 30000)]:
-        for mode in ("sync", "flag") * 2:
+        for mode in ("copy", "kernel") * 2:
             print(json.dumps(run(B, N, mode)), flush=True)
