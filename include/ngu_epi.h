@@ -168,7 +168,9 @@ int ngu_epi_step_rnd(ngu_epi* h, const float* q_dev, const float* pred_dev, cons
                      float* r_int_dev, float* r_epi_dev, float* alpha_out_dev, void* stream);
 
 /* Same, with HOST buffers (what the Python drop-in calls with CPU tensors):
- * H2D of q/alpha, the step, D2H of the rewards, synchronous. */
+ * H2D of q/alpha (from a pinned staging buffer: a PDL-chained kernel pulls it over PCIe on large
+ * shapes, the copy engine on small ones), the step, D2H of the rewards (written by the epilogue
+ * straight into mapped host memory), synchronous. */
 int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host,
                       float* r_int_host, float* r_epi_host);
 int ngu_epi_reset_host(ngu_epi* h, const uint8_t* done_host);
@@ -180,8 +182,14 @@ int ngu_epi_reset_host(ngu_epi* h, const uint8_t* done_host);
  * of this library's contract. */
 int ngu_epi_topk_host(ngu_epi* h, float* d2_host, int32_t* idx_host);
 
-int ngu_epi_get_state(ngu_epi* h, ngu_epi_state* out);      /* synchronous */
-int ngu_epi_set_state(ngu_epi* h, const ngu_epi_state* in); /* synchronous */
+/* Checkpoint / parity injection of the running statistics and the ring cursor.  Synchronous.
+ * The log-only trackers (epi_*, intr_*: episodic_novelty.py:82, intrinsic_novelty.py:32 - never read by
+ * the hot path) are kept off the step's critical path: a fused step (ngu_epi_step*, ngu_epi_step_host)
+ * stashes its rewards on the device and the next fused step folds them in while its scan runs.
+ * ngu_epi_get_state folds an outstanding stash in first, so what it returns is always up to date
+ * (single GPU; connected ranks call ngu_epi_log_flush first, below).  ngu_epi_set_state drops it. */
+int ngu_epi_get_state(ngu_epi* h, ngu_epi_state* out);
+int ngu_epi_set_state(ngu_epi* h, const ngu_epi_state* in);
 
 /* Bulk load / dump of the episodic memory in the REFERENCE layout
  * float[capacity][n_actors][32] on the host (tests, checkpoints).  Synchronous. */
@@ -198,7 +206,8 @@ int ngu_epi_dump_memory_host(ngu_epi* h, float* slot_major_host);
  * must sit on DISTINCT GPUs (the kernel polls words written by the peers).  The log-only sums
  * (epi_novel_rms, intrinsic_novel_rms; never read by the hot path) ride on the NEXT step's
  * exchange, so those two trackers lag one step; ngu_epi_log_flush (collective: every rank, same
- * point of its stream) brings them up to date before they are read.  A no-op unless connected. */
+ * point of its stream) brings them up to date before they are read.  Unconnected, it folds the
+ * outstanding reward stash into the trackers on `stream` (what ngu_epi_get_state does synchronously). */
 int ngu_epi_p2p_export(ngu_epi* h, void* ipc_handle_out, int32_t world);
 int ngu_epi_p2p_connect(ngu_epi* h, int32_t rank, int32_t world, const void* ipc_handles);
 int ngu_epi_log_flush(ngu_epi* h, void* stream);
