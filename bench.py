@@ -30,6 +30,22 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE line, the JSON result.  Libraries write there too (NCCL prints its
+# version banner on fd 1), so the real stdout is kept aside and fd 1 is pointed at stderr.
+RESULT_OUT = None
+
+
+def claim_stdout():
+    global RESULT_OUT
+    if RESULT_OUT is None:
+        sys.stdout.flush()
+        RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    print(json.dumps(line), file=RESULT_OUT or sys.stdout, flush=True)
+
 ACTORS_PER_GPU = 256
 CAPACITY = 30000
 K_NEIGHBORS = 10
@@ -142,7 +158,7 @@ def run_reference_arm(args, rank):
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------
@@ -270,7 +286,11 @@ def run_gpu_arm(args, rank, world, local_rank):
                            if sh.exchange == "p2p" else "21-double rank-sum all-reduce (torch.distributed) per step"),
                        "scan_geometry": geo},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 32 * 4 + B * 4,
-                    "d2h_bytes_per_step": 2 * B * 4 if host_call else B * 4},
+                    "d2h_bytes_per_step": 2 * B * 4 if host_call else B * 4,
+                    "path": ("ngu_epi_step_host per step, synchronous: q+alpha from a pinned host buffer (pulled over PCIe by "
+                             "a PDL-chained kernel, or the copy engine on small shapes), r_int+r_epi written by the epilogue "
+                             "into mapped host memory") if host_call else
+                            "pinned H2D copies + sharded step + D2H of the rewards per step, synchronous"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": achieved, "peak": peak,
@@ -284,7 +304,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                 "value": qps, "unit": UNIT, "cores": threads, "kind": "port",
                 "sample": f"{done} steps of the same {B} x {N} workload, torch-CPU op-for-op port of the reference "
                           f"(oracle/torch_port.py), {ms:.1f} ms/step"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -309,6 +329,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
+        claim_stdout()
         run_reference_arm(args, rank)
         return
     if world == 1 and args.gpus > 1:
@@ -318,6 +339,7 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"),
                os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    claim_stdout()
     run_gpu_arm(args, rank, world, local_rank)
 
 
