@@ -86,6 +86,8 @@ __device__ __noinline__ float np_pairwise_leaf8(const float* v, int stride, int 
 }
 
 constexpr int kPlanMaxDepth = 24;
+constexpr int kPlanMaxLeaves = 256;                     // n <= 128 * 256 rows per column sum
+constexpr int kPlanMaxEntries = 2 * kPlanMaxLeaves - 1; // postfix entries; the leaf list follows them in the plan buffer
 
 __device__ __forceinline__ float np_pairwise_sum8(const float* v, int stride, const int2* plan, int plan_len,
                                                   int lane8, float* stack /* [kPlanMaxDepth] per thread */) {
@@ -134,11 +136,11 @@ struct EpilogueParams {
     const float* q;           // [B][32] (APPEND)
     float* memory;            // [B][N][32] (APPEND)
     DevState* state;
-    const int2* plan;         // pairwise-sum plan for n = B
+    const int2* plan;         // pairwise-sum plan for n = B: plan_len postfix entries, then the n_leaves leaves in order
     int32_t plan_len;
     int32_t phases;
     int32_t stage_q;          // 1: q fits the dynamic shared memory of this launch
-    int32_t pad;
+    int32_t n_leaves;
     const float* rnd_pred;    // [B][128] RND predictor features (PH_RND)
     const float* rnd_targ;    // [B][128] RND target features
     float* alpha_out;         // [B] or null: the modulator computed by the RND phase
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
     __shared__ double red[4][THREADS / 32];
     __shared__ long long s_cursor;
     __shared__ double s_log[8];
-    __shared__ int2 s_plan[64];
+    __shared__ int2 s_plan[kPlanMaxEntries + kPlanMaxLeaves];
     __shared__ float s_stack[256][kPlanMaxDepth + 1];   // value stacks of the rank-sum threads (padded)
     extern __shared__ float s_dyn[];
     const int k = c.k;
@@ -372,7 +374,8 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
     if (append) {
         if (threadIdx.x == 64) s_cursor = __ldcg(&st->cursor);
     }
-    if (threadIdx.x >= 96 && threadIdx.x < 96 + p.plan_len && threadIdx.x < 160) s_plan[threadIdx.x - 96] = __ldcg(p.plan + (threadIdx.x - 96));
+#pragma unroll 1
+    for (int i = threadIdx.x; i < p.plan_len + p.n_leaves; i += THREADS) s_plan[i] = __ldcg(p.plan + i);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     EPI_STAMP(1);
@@ -422,12 +425,22 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
     }
 
     if (p.phases & PH_RANKSUMS) {
+        float* s_leafsum = &s_stack[64][0];                        // [k][n_leaves]; stacks 0..31 serve the fold below
         if (threadIdx.x < 256) {
-            // column sums in numpy's pairwise order: 8 lanes per column (whole warps: shuffles inside)
+            // column sums in numpy's pairwise order.  Every (column, leaf) pair is an independent sum of
+            // <= 128 rows: 8 lanes own numpy's 8 strided accumulators (whole warps: shuffles inside), the
+            // 32 groups of 8 lanes take the pairs round robin - one round at 256 actors (10 x 2 pairs).
             const int group = threadIdx.x >> 3, lane8 = threadIdx.x & 7;
-            const int j = group < k ? group : k - 1;                   // idle groups shadow column k-1
-            const float s1 = np_pairwise_sum8(s_dist + j, k, s_plan, p.plan_len, lane8, s_stack[threadIdx.x]);
-            if (group < k && lane8 == 0) s_sums[group] = static_cast<double>(s1);
+            const int L = p.n_leaves, items = k * L;
+#pragma unroll 1
+            for (int w0 = 0; w0 < items; w0 += 32) {
+                const int w = w0 + group;
+                const int wc = w < items ? w : items - 1;              // idle groups shadow the last pair
+                const int j = wc / L, l = wc - j * L;
+                const int2 e = s_plan[p.plan_len + l];
+                const float s1 = np_pairwise_leaf8(s_dist + j + e.x * k, k, e.y, lane8);
+                if (w < items && lane8 == 0) s_leafsum[wc] = s1;
+            }
         } else {
             // meanwhile: f64 sums of squares (for the log-only variance), a full warp per column
             const int lane = threadIdx.x & 31;
@@ -443,6 +456,23 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
                 for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(kFull, s2, o);
                 if (lane == 0) s_sums[k + j] = s2;
             }
+        }
+        __syncthreads();
+        if (threadIdx.x < k) {
+            // fold the leaf sums of column j along numpy's recursion (the postfix plan)
+            float* stack = s_stack[threadIdx.x];
+            const float* leaf = s_leafsum + threadIdx.x * p.n_leaves;
+            int sp = 0;
+#pragma unroll 1
+            for (int i = 0; i < p.plan_len; ++i) {
+                if (s_plan[i].y > 0) {
+                    stack[sp++] = *leaf++;
+                } else {
+                    --sp;
+                    stack[sp - 1] = __fadd_rn(stack[sp - 1], stack[sp]);
+                }
+            }
+            s_sums[threadIdx.x] = static_cast<double>(stack[0]);
         }
         if (threadIdx.x == 0) s_sums[2 * k] = static_cast<double>(B);
         __syncthreads();

@@ -107,8 +107,8 @@ struct ngu_epi {
     int sched_c2 = 16;                       // tiles per dynamic chunk
     int sched_min_avg = kDynMinAvgTilesDefault;   // fair share (tiles per warp) below which the schedule is static only
     int sched_min_tiles = kMinTilesPerWarp;       // static-only schedules: at least this many tiles per warp
-    int2* plan_dev = nullptr;        // pairwise-sum plan for n = B (epilogue rank sums)
-    int plan_len = 0;
+    int2* plan_dev = nullptr;        // pairwise-sum plan for n = B (epilogue rank sums): postfix entries, then the leaves
+    int plan_len = 0, plan_leaves = 0;
     // p2p rank-sum exchange (multi-GPU): local inbox + IPC-mapped peer inboxes
     unsigned long long* inbox = nullptr;
     P2PView p2p{};
@@ -381,6 +381,15 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
         std::vector<int2> plan;
         build_pairwise_plan(0, B, plan);
         h->plan_len = static_cast<int>(plan.size());
+        for (int i = 0; i < h->plan_len; ++i)
+            if (plan[i].y > 0) plan.push_back(plan[i]);
+        h->plan_leaves = static_cast<int>(plan.size()) - h->plan_len;
+        if (h->plan_leaves > kPlanMaxLeaves || h->plan_len > kPlanMaxEntries) {
+            g_create_error = fmt("n_actors=%d needs %d pairwise-sum leaves, the epilogue holds %d; shard the actors", B,
+                                 h->plan_leaves, kPlanMaxLeaves);
+            ngu_epi_destroy(h);
+            return NGU_EINVAL;
+        }
         CREATE_TRY(cudaMalloc(&h->plan_dev, plan.size() * sizeof(int2)));
         CREATE_TRY(cudaMemcpy(h->plan_dev, plan.data(), plan.size() * sizeof(int2), cudaMemcpyHostToDevice));
     }
@@ -512,7 +521,7 @@ static int launch_epilogue(ngu_epi* h, int phases, const double* sums_in, const 
         ep.phases |= PH_EXCHANGE;
         ep.p2p = h->p2p;
     }
-    ep.plan = h->plan_dev; ep.plan_len = h->plan_len;
+    ep.plan = h->plan_dev; ep.plan_len = h->plan_len; ep.n_leaves = h->plan_leaves;
     ep.log_stash = h->log_stash;
     // dynamic smem: [dist B*k][alpha B][q B*32] when it all fits, else without q
     ep.stage_q = epilogue_smem_bytes(h->cfg.n_actors, h->cfg.k, true) <= kEpilogueStageBytes ? 1 : 0;

@@ -50,7 +50,9 @@ def test_golden_trajectory(cuda_device, name, variant):
 
 @pytest.mark.parametrize("B,N,k,mode", [(16, 3000, 10, "reference"), (3, 1000, 1, "reference"),
                                          (5, 2049, 32, "reference"), (9, 4097, 10, "paper"),
-                                         (2, 33, 10, "reference"), (1, 30000, 10, "reference")])
+                                         (2, 33, 10, "reference"), (1, 30000, 10, "reference"),
+                                         # many actors: the pairwise rank sums have 8 / 64 leaves per column
+                                         (1024, 100, 10, "reference"), (5000, 40, 4, "reference")])
 def test_random_vs_oracle(cuda_device, B, N, k, mode):
     from ngu_b200.engine import EpisodicEngine
     from oracle.episodic_oracle import EpisodicOracle
