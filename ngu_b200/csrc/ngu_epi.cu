@@ -105,6 +105,7 @@ struct ngu_epi {
     ScanSched sched{};
     double sched_static_frac = 0.6;          // share of the tiles handed out statically (experiments: NGU_EPI_SCHED=frac,c2)
     int sched_c2 = 16;                       // tiles per dynamic chunk
+    double taper_half = 0.0, taper_quarter = 0.0;   // share of a matrix row cut into c2/2 and c2/4 chunks (NGU_EPI_TAPER=h,q)
     int sched_min_avg = kDynMinAvgTilesDefault;   // fair share (tiles per warp) below which the schedule is static only
     int sched_min_tiles = kMinTilesPerWarp;       // static-only schedules: at least this many tiles per warp
     int2* plan_dev = nullptr;        // pairwise-sum plan for n = B (epilogue rank sums): postfix entries, then the leaves
@@ -208,7 +209,7 @@ void plan_geometry(ngu_epi* h) {
     ScanSched& sc = h->sched;
     sc = ScanSched{};
     sc.total_tiles = static_cast<int32_t>(T);
-    sc.c2 = 1; sc.rows = 1; sc.cols = 0;
+    sc.c2 = 1; sc.rows = 1; sc.cols = 0; sc.row_tiles = 1;
     int min_chunk;
     if (T < h->sched_min_avg * max_warps || h->sched_static_frac >= 1.0 || h->sched_c2 <= 0) {
         int64_t tpw = (T + max_warps - 1) / max_warps;
@@ -227,10 +228,21 @@ void plan_geometry(ngu_epi* h) {
         sc.s1 = s1 >= 1 ? static_cast<int32_t>(s1) : 1;
         const int64_t rest = T - static_cast<int64_t>(sc.n1) * sc.s1;
         sc.c2 = c2;
-        sc.n2 = static_cast<int32_t>((rest + c2 - 1) / c2);
-        sc.cols = h->tiles_per_actor / c2 > 0 ? h->tiles_per_actor / c2 : 1;   // ~ chunks per actor
-        sc.rows = (sc.n2 + sc.cols - 1) / sc.cols;
-        min_chunk = static_cast<int>(sc.n1 > 0 && sc.s1 < c2 ? sc.s1 : c2);
+        const int wide = h->tiles_per_actor / c2 > 0 ? h->tiles_per_actor / c2 : 1;   // ~ chunks per actor, untapered
+        int cb = 0, cc = 0;
+        if (c2 % 4 == 0 && wide >= 8) {      // taper: the last shares of a row in half and quarter chunks
+            cb = static_cast<int>(h->taper_half * wide) * 2;
+            cc = static_cast<int>(h->taper_quarter * wide) * 4;
+            if (cb / 2 + cc / 4 > wide - 1) { cb = 0; cc = 0; }
+        }
+        sc.cols_a = wide - cb / 2 - cc / 4;
+        sc.cols_b = cb;
+        sc.cols = sc.cols_a + cb + cc;
+        sc.row_tiles = sc.cols_a * c2 + cb * (c2 / 2) + cc * (c2 / 4);        // = wide * c2
+        sc.rows = static_cast<int32_t>((rest + sc.row_tiles - 1) / sc.row_tiles);
+        if (sc.rows < 1) sc.rows = 1;
+        const int narrow = cc ? c2 / 4 : cb ? c2 / 2 : c2;
+        min_chunk = static_cast<int>(sc.n1 > 0 && sc.s1 < narrow ? sc.s1 : narrow);
         sc.n_chunks = sc.n1 + sc.rows * sc.cols;
     }
     // worst case every run publishes k candidates; runs per actor <= chunks overlapping it
@@ -245,6 +257,12 @@ void apply_sched_env(ngu_epi* h) {
         if (got >= 2) h->sched_c2 = c2;
         if (got >= 3 && mn >= 0) h->sched_min_avg = mn;
         if (got >= 4 && mt >= 1) h->sched_min_tiles = mt;
+    }
+    if (const char* e = getenv("NGU_EPI_TAPER")) {   // experiments: "half_share,quarter_share" of every matrix row
+        double a = 0.0, b = 0.0;
+        const int got = sscanf(e, "%lf,%lf", &a, &b);
+        if (got >= 1 && a >= 0.0 && a < 1.0) h->taper_half = a;
+        if (got >= 2 && b >= 0.0 && b < 1.0) h->taper_quarter = b;
     }
 }
 

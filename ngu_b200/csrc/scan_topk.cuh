@@ -36,9 +36,9 @@
 //     its last tile it takes merge jobs (one actor each) and merges that actor's candidates
 //     incrementally, as they are published, into the final k-NN (d^2, slot, dist): the merges
 //     overlap the end of the stream, and no separate merge launch sits on the critical path.
-//   * programmatic dependent launch: the kernel lets its dependent (the epilogue
-//     kernel) get resident immediately and itself waits on its predecessor only
-//     right before the first TMA load (griddepcontrol).
+//   * programmatic dependent launch: the kernel waits on its predecessor only right before
+//     the first TMA load (griddepcontrol), after having prefetched its first tiles into L2, and
+//     then lets its dependent (the epilogue kernel) become resident.
 //
 // Arithmetic order (bit-exact with torch 2.11 CPU):
 //   diff = m - q ; s = diff*diff (separately rounded, no FMA);
@@ -64,12 +64,18 @@ namespace ngu {
 // dynamic counter hands out the indices above.  Indices whose natural chunk is >= n2 are empty.
 // (Measured on B200, 256 x 30k: s1 = 60 % of the fair share and c2 = 16 tiles; smaller chunks pay
 // more in flushes than they win at the ragged end, and tapering the last chunks did not pay either.)
+// A row of the matrix may taper (experiment knob NGU_EPI_TAPER, default off): its first cols_a chunks have c2
+// tiles, the next cols_b have c2/2, the rest c2/4.  Handing out column by column, the narrow chunks are the last
+// ones of the launch, so the warps run dry within one SHORT chunk of each other (a full chunk is ~22 us of one
+// warp's time at 256 x 30k).  Measured: no gain at 256 x 30k - the extra run starts cost what the sharper end
+// wins ("Measured and rejected").
 struct ScanSched {
     int32_t total_tiles;     // B * tiles_per_actor
     int32_t n_chunks;        // n1 + rows * cols
     int32_t n1, s1;
-    int32_t n2, c2;
+    int32_t row_tiles, c2;   // tiles per matrix row = cols_a*c2 + cols_b*(c2/2) + (cols - cols_a - cols_b)*(c2/4)
     int32_t rows, cols;
+    int32_t cols_a, cols_b;
 };
 
 __host__ __device__ __forceinline__ void chunk_range(const ScanSched& s, int idx, int& t, int& te) {
@@ -79,10 +85,18 @@ __host__ __device__ __forceinline__ void chunk_range(const ScanSched& s, int idx
     } else {
         const int i = idx - s.n1;
         const int c = i / s.rows;
-        const int j = (i - c * s.rows) * s.cols + c;
-        if (j >= s.n2) { t = 0; te = 0; return; }
-        t = s.n1 * s.s1 + j * s.c2;
-        te = t + s.c2;
+        const int r = i - c * s.rows;
+        int off, len;
+        if (c < s.cols_a) {
+            off = c * s.c2; len = s.c2;
+        } else if (c < s.cols_a + s.cols_b) {
+            off = s.cols_a * s.c2 + (c - s.cols_a) * (s.c2 >> 1); len = s.c2 >> 1;
+        } else {
+            off = s.cols_a * s.c2 + s.cols_b * (s.c2 >> 1) + (c - s.cols_a - s.cols_b) * (s.c2 >> 2); len = s.c2 >> 2;
+        }
+        t = s.n1 * s.s1 + r * s.row_tiles + off;
+        if (t >= s.total_tiles) { t = 0; te = 0; return; }
+        te = t + len;
     }
     if (te > s.total_tiles) te = s.total_tiles;
 }

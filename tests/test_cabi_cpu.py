@@ -101,8 +101,9 @@ def test_actor_partition():
     assert actor_partition(10, 4) == [0, 3, 6, 8, 10]
 
 
-@pytest.mark.parametrize("sched", [None, "0.5,2,1", "0.0,3,1", "0.3,8,1,2", "1.0,0"])
-def test_scan_schedule_partitions_the_tile_space_host_side(lib, monkeypatch, sched):
+@pytest.mark.parametrize("sched,taper", [(None, None), ("0.5,2,1", None), ("0.0,3,1", None), ("0.3,8,1,2", None), ("1.0,0", None),
+                                         (None, "0.2,0.1"), ("0.5,8,1", "0.3,0.3"), ("0.0,4,1", "0.0,0.5"), (None, "0.9,0.0")])
+def test_scan_schedule_partitions_the_tile_space_host_side(lib, monkeypatch, sched, taper):
     """Host logic of the scan kernel's work schedule (plan_geometry + chunk_range, no GPU needed): for
     many shapes, SM counts and kernel geometries every tile is handed out exactly once, the grid is one
     wave at most, and the statically owned chunks are the first ones."""
@@ -112,6 +113,10 @@ def test_scan_schedule_partitions_the_tile_space_host_side(lib, monkeypatch, sch
         monkeypatch.setenv("NGU_EPI_SCHED", sched)
     else:
         monkeypatch.delenv("NGU_EPI_SCHED", raising=False)
+    if taper:                         # rows of the dynamic matrix end in half / quarter chunks
+        monkeypatch.setenv("NGU_EPI_TAPER", taper)
+    else:
+        monkeypatch.delenv("NGU_EPI_TAPER", raising=False)
     rng = np.random.default_rng(0)
     shapes = [(256, 30000), (1024, 30000), (1, 30000), (64, 5000), (37, 777), (3, 10), (5000, 33), (1, 10), (4096, 1000)]
     shapes += [(int(rng.integers(1, 600)), int(rng.integers(10, 40000))) for _ in range(12)]
