@@ -4,8 +4,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from ngu_b200.engine import EpisodicEngine
 
+KNOB = sys.argv[1] if len(sys.argv) > 1 else "NGU_EPI_HOST_STAGE"
+MODES = tuple(sys.argv[2].split(",")) if len(sys.argv) > 2 else ("copy", "kernel")
+
+
 def run(B, N, mode, steps=300):
-    os.environ["NGU_EPI_HOST_STAGE"] = mode
+    os.environ[KNOB] = mode
     eng = EpisodicEngine(B, N, device=0)
     eng._memory.normal_()
     rng = np.random.default_rng(0)
@@ -23,5 +27,5 @@ def run(B, N, mode, steps=300):
 
 if __name__ == "__main__":
     for (B, N) in [(256, 30000), (64, 5000), (1, 30000), (32, 30000), (1024, 30000)]:
-        for mode in ("copy", "kernel") * 2:
+        for mode in MODES * 2:
             print(json.dumps(run(B, N, mode)), flush=True)

@@ -29,8 +29,19 @@ def run(B, N, env, steps=600):
     for i in range(200): eng.step(qs[i % 8], al[i % 8])
     ms, n = eng.scan_timing_end()
     assert eng.get_state()["exchange_timeouts"] == 0
+    # host-buffer path (ngu_epi_step_host), synchronous per step
+    import time, numpy as np
+    rng = np.random.default_rng(0)
+    qh = [rng.standard_normal((B, 32), dtype=np.float32) for _ in range(8)]
+    ah = [(1 + rng.standard_normal(B)).astype(np.float32) for _ in range(8)]
+    for i in range(50): eng.step_host(qh[i % 8], ah[i % 8])
+    host = 1e9
+    for rep in range(3):
+        t0 = time.perf_counter()
+        for i in range(300): eng.step_host(qh[i % 8], ah[i % 8])
+        host = min(host, (time.perf_counter() - t0) / 300 * 1e6)
     eng.close()
-    return dict(B=B, N=N, env=env, step_us=round(us, 2), scan_alone_us=round(ms / n * 1e3, 2))
+    return dict(B=B, N=N, env=env, step_us=round(us, 2), scan_alone_us=round(ms / n * 1e3, 2), host_step_us=round(host, 2))
 
 if __name__ == "__main__":
     B, N, reps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
