@@ -292,8 +292,8 @@ __device__ __forceinline__ void consume_candidates(const ScanParams& p, const u6
 // the first rank, and as soon as a whole rank fails it the deeper (smaller) ranks cannot pass either: a
 // merge touches 2-3 ranks and does ~15 insertions, where storage order does ~10 ln(rows / 10) of them
 // (~200 cycles each, one warp) plus a threshold pass.
-__device__ __forceinline__ void consume_lists(const ScanParams& p, const u64* cand, int nlists, uint32_t tag, int lane,
-                                              uint32_t stage /* 8 KB smem */, WarpTopK& m) {
+__device__ __forceinline__ void consume_lists_staged(const ScanParams& p, const u64* cand, int nlists, uint32_t tag, int lane,
+                                                     uint32_t stage /* 8 KB smem */, WarpTopK& m) {
     const int k = p.k;
     const int per_round = 512 / k;                        // whole lists per staging round
     for (int l0 = 0; l0 < nlists; l0 += per_round) {
@@ -310,6 +310,139 @@ __device__ __forceinline__ void consume_lists(const ScanParams& p, const u64* ca
                 m.offer(key, lane, k);
             }
             if (!passed) break;
+        }
+    }
+}
+
+// MANY lists (an actor cut into hundreds of runs: 1 x 30 000 is 235 lists, 2 350 keys): staging everything
+// costs a round trip per 51 lists and ~25 mostly useless batches (11 us, two fifths of such a step).
+// Threshold first instead:
+//   1. gather only the BEST key of every list (one round trip, lane l owns lists l, l+32, ...);
+//   2. the k-th largest of the 32 lane maxima is a real key with >= k candidates at or above it: everything
+//      below it is out (the list's floor) - one bitonic sort;
+//   3. compact the survivors into a small buffer (ballot + popc), offer them 32 at a time: the threshold is
+//      now the true k-th best of the rank-0 keys;
+//   4. a list stays alive while its last key passed (lists are sorted): per rank, the alive lists' next keys
+//      are gathered in one round trip; two or three ranks and a few dozen offered keys in all.
+__device__ __forceinline__ u64 warp_sort_desc(u64 x, int lane) {
+#pragma unroll 1
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll 1
+        for (int j = size >> 1; j > 0; j >>= 1) {
+            const u64 o = __shfl_xor_sync(kFull, x, j);
+            const bool desc_block = (lane & size) == 0;
+            const bool lower = (lane & j) == 0;
+            x = (lower == desc_block) ? umax64(x, o) : umin64(x, o);
+        }
+    }
+    return x;
+}
+__device__ __forceinline__ void consume_lists(const ScanParams& p, const u64* cand, int nlists, uint32_t tag, int lane,
+                                              uint32_t stage /* 8 KB smem */, WarpTopK& m) {
+    const int k = p.k;
+    if (nlists * k <= 512 || nlists < 64) {               // everything fits one or two staging rounds
+        consume_lists_staged(p, cand, nlists, tag, lane, stage, m);
+        return;
+    }
+    constexpr int kRound = 384;                           // lists per round: 6 KB of 16-byte entries, 12 per lane
+    constexpr int kBuf = 256;                             // compacted keys (2 KB) behind them
+    const uint32_t buf = stage + kRound * 16;
+    const unsigned lt = (1u << lane) - 1u;
+    int nbuf = 0;                                         // warp-uniform
+    auto drain = [&]() {
+        __syncwarp();
+#pragma unroll 1
+        for (int e0 = 0; e0 < nbuf; e0 += 32) {
+            u64 key = 0ull;
+            if (e0 + lane < nbuf) asm volatile("ld.shared.u64 %0, [%1];" : "=l"(key) : "r"(buf + (e0 + lane) * 8) : "memory");
+            m.offer(key, lane, k);
+        }
+        nbuf = 0;
+        __syncwarp();
+    };
+    auto push = [&](u64 key, bool q) {                    // all lanes; q: this lane's key goes in
+        const unsigned bal = __ballot_sync(kFull, q);
+        if (bal) {
+            if (q) asm volatile("st.shared.u64 [%0], %1;" ::"r"(buf + (nbuf + __popc(bal & lt)) * 8), "l"(key) : "memory");
+            nbuf += __popc(bal);
+            if (nbuf + 32 > kBuf) drain();
+        }
+    };
+#pragma unroll 1
+    for (int l0 = 0; l0 < nlists; l0 += kRound) {
+        const int nl = nlists - l0 < kRound ? nlists - l0 : kRound;
+        const u64* base = cand + static_cast<int64_t>(l0) * k * 2;
+        // rank 0 of every list of the round: one gather, every lane reads back only what it copied itself
+#pragma unroll 1
+        for (int i = lane; i < nl; i += 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage + i * 16), "l"(base + static_cast<int64_t>(i) * k * 2)
+                         : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        u64 mx = 0ull;
+#pragma unroll 1
+        for (int i = lane; i < nl; i += 32) {
+            u64 w0, w1;
+            lds_2x64(stage + i * 16, w0, w1);
+            int polls = 0;
+            while (!ll_ready(w0, w1, tag)) {
+                ld_ll_raw(base + static_cast<int64_t>(i) * k * 2, w0, w1);
+                if (++polls > kLLSpinLimit) { atomicAdd(p.timeouts, 1ull); w0 = 0ull; w1 = 0ull; break; }
+            }
+            const u64 key = (w0 & 0xFFFFFFFF00000000ull) | (w1 >> 32);
+            asm volatile("st.shared.u64 [%0], %1;" ::"r"(stage + i * 16), "l"(key) : "memory");   // resolved key, in place
+            mx = umax64(mx, key);
+        }
+        const u64 kth = __shfl_sync(kFull, warp_sort_desc(mx, lane), k - 1);
+        if (kth > 1ull && kth - 1ull > m.thr) {           // >= k real keys are >= kth: nothing below it can make the top k
+            m.floor = umax64(m.floor, kth - 1ull);
+            m.thr = umax64(m.thr, m.floor);
+        }
+        unsigned alive = 0u;                              // bit j: list lane + 32 j of this round may still have a key that passes
+#pragma unroll 1
+        for (int j = 0; 32 * j < nl; ++j) {
+            const int i = lane + 32 * j;
+            u64 key = 0ull;
+            if (i < nl) asm volatile("ld.shared.u64 %0, [%1];" : "=l"(key) : "r"(stage + i * 16) : "memory");
+            const bool q = key > m.thr;
+            if (q) alive |= 1u << j;
+            push(key, q);
+        }
+        drain();                                          // thr = the k-th best of the rank-0 keys
+#pragma unroll 1
+        for (int r = 1; r < k; ++r) {
+            if (!__any_sync(kFull, alive != 0u)) break;
+#pragma unroll 1
+            for (int j = 0; 32 * j < nl; ++j)             // the alive lists' next keys: one gather
+                if ((alive >> j) & 1u) {
+                    const int i = lane + 32 * j;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage + i * 16),
+                                 "l"(base + (static_cast<int64_t>(i) * k + r) * 2)
+                                 : "memory");
+                }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll 1
+            for (int j = 0; 32 * j < nl; ++j) {
+                if (!__any_sync(kFull, (alive >> j) & 1u)) continue;
+                const bool a = (alive >> j) & 1u;
+                u64 key = 0ull;
+                if (a) {
+                    const int i = lane + 32 * j;
+                    u64 w0, w1;
+                    lds_2x64(stage + i * 16, w0, w1);
+                    int polls = 0;
+                    while (!ll_ready(w0, w1, tag)) {
+                        ld_ll_raw(base + (static_cast<int64_t>(i) * k + r) * 2, w0, w1);
+                        if (++polls > kLLSpinLimit) { atomicAdd(p.timeouts, 1ull); w0 = 0ull; w1 = 0ull; break; }
+                    }
+                    key = (w0 & 0xFFFFFFFF00000000ull) | (w1 >> 32);
+                }
+                const bool q = key > m.thr;
+                if (a && !q) alive &= ~(1u << j);
+                push(key, q);
+            }
+            drain();
         }
     }
 }

@@ -1,5 +1,5 @@
 """Scratch: device-resident step time for a list of environment-knob settings, interleaved repeats on one box.
-  python tools/knob_sweep.py B N REPEATS KEY=v1,KEY2=v2 KEY=v3 ...      ("-" = no knob)"""
+  python tools/knob_sweep.py B N REPEATS KEY=v1;KEY2=v2 KEY=v3 ...      ("-" = no knob)"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -45,7 +45,7 @@ def run(B, N, env, steps=600):
 
 if __name__ == "__main__":
     B, N, reps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
-    cases = [dict(kv.split("=", 1) for kv in a.split(",")) if a != "-" else {} for a in sys.argv[4:]]
+    cases = [dict(kv.split("=", 1) for kv in a.split(";")) if a != "-" else {} for a in sys.argv[4:]]
     for rep in range(reps):
         for env in cases:
             print(json.dumps(run(B, N, env)), flush=True)
