@@ -620,7 +620,8 @@ static int step_impl(ngu_epi* h, const float* q_dev, const float* alpha_dev, flo
                      cudaStream_t s, const HostFlag* hf) {
     int rc = launch_scan(h, q_dev, s);
     if (rc) return rc;
-    // one epilogue launch: rank sums -> running-mean update -> rewards -> log-only stats -> append
+    // one epilogue launch: rank sums -> running-mean update -> rewards (stashed for the log-only trackers, which the
+    // next fused launch brings up to date: epilogue.cuh, log_absorb) -> append
     return launch_epilogue(h, PH_RANKSUMS | PH_FINISH | PH_APPEND | PH_LOGFUSE, nullptr, alpha_dev, r_int_dev,
                            r_epi_dev, nullptr, q_dev, s, nullptr, hf);
 }
