@@ -58,12 +58,25 @@ class IntrinsicNovelty:
             out = self._graphed(obs)
             self.epi_novel._memory_idx = (self.epi_novel._memory_idx + 1) % self.epi_novel.capacity
             return out
-        obs_dev = obs.to(eng.device, non_blocking=True)
+        obs_dev = self._obs_to_device(obs, eng.device)
         pred, targ = self.ll_novel(obs_dev)                            # lifelong_novelty.py:52
         q = self.epi_novel._embed(obs_dev)                             # episodic_novelty.py:47
         r_int, _, _ = eng.step_rnd(q, pred, targ)
         self.epi_novel._memory_idx = (self.epi_novel._memory_idx + 1) % self.epi_novel.capacity
         return r_int.cpu().unsqueeze(-1)
+
+    def _obs_to_device(self, obs, device):
+        """One host->device copy of the observations for both CNN stacks.  A large PAGEABLE batch (what an
+        env wrapper hands over) goes through a persistent pinned buffer: 0.21 ms instead of 0.39 ms for the
+        7.2 MB of 256 actors (tools/obs_h2d_probe.py); small or already pinned batches are copied directly.
+        The call is synchronous (it ends with the reward read-back), so the buffer is free again on return."""
+        if obs.device.type != "cpu" or obs.is_pinned() or obs.dtype != torch.float32 or obs.numel() < (1 << 18):
+            return obs.to(device, non_blocking=True)
+        buf = getattr(self, "_obs_pinned", None)
+        if buf is None or buf.shape != obs.shape:
+            buf = self._obs_pinned = torch.empty(obs.shape, dtype=torch.float32).pin_memory()
+        buf.copy_(obs)
+        return buf.to(device, non_blocking=True)
 
     def reset_memory_if_done(self, done):
         """intrinsic_novelty.py:36-40: zero the episodic memory of finished actors."""

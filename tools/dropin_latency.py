@@ -12,13 +12,15 @@ class L:
     def log_scalar(self, *a): pass
 
 
-def run(B, N, graph, steps=100):
+def run(B, N, graph, steps=100, pinned=False):
     ptu.init_device()
     inn = IntrinsicNovelty(B, 18, (1, 84, 84), dict(DEFAULT_HYPR, episodic_memory_capacity=N), L()).to(ptu.device)
     inn.epi_novel._ensure_engine()._memory.normal_()
     if graph:
         inn.enable_cuda_graph()
-    obs = [torch.randn(B, 1, 84, 84).clamp_(-5, 5).pin_memory() for _ in range(4)]
+    obs = [torch.randn(B, 1, 84, 84).clamp_(-5, 5) for _ in range(4)]       # pageable, as an env wrapper hands them over
+    if pinned:
+        obs = [o.pin_memory() for o in obs]
     for i in range(10):
         inn.compute_intrinsic_novelty(obs[i % 4])
     torch.cuda.synchronize()
@@ -27,10 +29,10 @@ def run(B, N, graph, steps=100):
         inn.compute_intrinsic_novelty(obs[i % 4])
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
-    return dict(B=B, N=N, graph=graph, ms_per_step=round(dt * 1e3, 4), qps=round(B / dt))
+    return dict(B=B, N=N, graph=graph, pinned_obs=pinned, ms_per_step=round(dt * 1e3, 4), qps=round(B / dt))
 
 
 if __name__ == "__main__":
     for B, N in [(256, 30000), (64, 5000), (1, 30000)]:
-        for graph in (False, True):
-            print(json.dumps(run(B, N, graph)), flush=True)
+        for graph, pinned in ((False, False), (False, True), (True, False)):
+            print(json.dumps(run(B, N, graph, pinned=pinned)), flush=True)
