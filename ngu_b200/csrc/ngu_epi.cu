@@ -609,8 +609,8 @@ int ngu_epi_reset(ngu_epi* h, const uint8_t* done_dev, void* stream) {
     int rc = bind_device(h);
     if (rc) return rc;
     const int64_t n4 = static_cast<int64_t>(h->cfg.capacity) * 8;
-    dim3 grid(static_cast<unsigned>((n4 + 2047) / 2048), h->cfg.n_actors);
-    reset_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->memory, done_dev, h->cfg.capacity);
+    dim3 grid(static_cast<unsigned>((n4 + 2047) / 2048), h->cfg.n_actors < kResetGroups ? h->cfg.n_actors : kResetGroups);
+    reset_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->memory, done_dev, h->cfg.n_actors, h->cfg.capacity);
     CU_TRY(h, cudaGetLastError());
     h->launches += 1;
     return NGU_OK;

@@ -130,7 +130,12 @@ class EpisodicEngine:
         check(self._lib.ngu_epi_append(self._h, _ptr(self._q_keep), self._stream()), self._h)
 
     def reset(self, done: torch.Tensor):
-        done = done.to(device=self.device).to(torch.uint8).contiguous()
+        done = done.to(device=self.device)
+        if done.dtype == torch.bool:
+            done = done.view(torch.uint8)            # same bytes (0 / 1): no cast kernel on the step's critical path
+        elif done.dtype != torch.uint8:
+            done = (done != 0).view(torch.uint8)
+        done = done.contiguous()
         self._done_keep = done
         check(self._lib.ngu_epi_reset(self._h, _ptr(done), self._stream()), self._h)
 
