@@ -80,9 +80,13 @@ class IntrinsicNovelty:
 
     def reset_memory_if_done(self, done):
         """intrinsic_novelty.py:36-40: zero the episodic memory of finished actors."""
-        done = torch.as_tensor(done)
-        if bool(done.any()):
-            self.epi_novel._ensure_engine().reset(done)
+        eng = self.epi_novel._ensure_engine()
+        if torch.is_tensor(done) and done.device.type != "cpu":
+            eng.reset(done)                       # device mask: stays on the stream, no host round trip
+            return
+        d = done.detach().numpy() if torch.is_tensor(done) else np.asarray(done)
+        if d.any():                               # the common step: nobody is done, nothing is launched
+            eng.reset_host(d)                     # pinned staging + reset kernel, synchronous
 
     def to(self, device):
         self.epi_novel.to(device)
