@@ -19,7 +19,8 @@ How the reference is driven:
   * Recorded per step: reference rewards (f64 under numpy>=2), the values of the
     reference's own ``topk`` on d^2, canonical indices (stable descending sort of
     the reference's distance expression; torch's own tie order is unspecified),
-    and the ``ed_rms`` state.
+    the ``ed_rms`` state and the two log-only trackers (``epi_novel_rms``,
+    ``intrinsic_novel_rms``).
 
 Usage:  python tests/golden/make_golden.py        (writes next to this file)
 """
@@ -111,7 +112,7 @@ def run_case(torch, IntrinsicNovelty, model_hypr, name, B, N, steps, seed, scale
         en.episodic_memory = torch.from_numpy(mem_init.copy())
     mem0 = en.episodic_memory.numpy().copy()
 
-    rec = {k_: [] for k_ in ("q", "alpha", "done", "reward", "d2", "idx", "mean", "var", "count")}
+    rec = {k_: [] for k_ in ("q", "alpha", "done", "reward", "d2", "idx", "mean", "var", "count", "epi_rms", "intr_rms")}
     for _ in range(steps):
         q = torch.randn(B, 32, generator=g) * scale
         alpha = np.ones(B) if alpha_kind == "ones" else 1.0 + 2.0 * rng.standard_normal(B)
@@ -133,6 +134,11 @@ def run_case(torch, IntrinsicNovelty, model_hypr, name, B, N, steps, seed, scale
         rec["mean"].append(np.broadcast_to(en.ed_rms.mean, (k,)).astype(np.float64).copy())
         rec["var"].append(np.broadcast_to(np.ravel(en.ed_rms.var), (k,)).astype(np.float64).copy())
         rec["count"].append(float(np.ravel(en.ed_rms.count)[0]))
+        # the log-only trackers (episodic_novelty.py:82, intrinsic_novelty.py:32): (mean, var, count) after the step
+        rec["epi_rms"].append(np.array([np.ravel(t)[0] for t in (en.epi_novel_rms.mean, en.epi_novel_rms.var,
+                                                                 en.epi_novel_rms.count)], np.float64))
+        rec["intr_rms"].append(np.array([np.ravel(t)[0] for t in (inn.intrinsic_novel_rms.mean, inn.intrinsic_novel_rms.var,
+                                                                  inn.intrinsic_novel_rms.count)], np.float64))
     out = {k_: np.stack(v) for k_, v in rec.items()}
     out["mem0"] = mem0
     out["mem_final"] = en.episodic_memory.numpy().copy()

@@ -37,6 +37,9 @@ def test_golden_trajectory(cuda_device, name, variant):
         np.testing.assert_allclose(st["ed_mean"], g["mean"][t], rtol=1e-6)
         np.testing.assert_allclose(st["ed_var"], g["var"][t], rtol=1e-4, atol=1e-9)
         assert st["ed_count"] == g["count"][t]
+        # log-only trackers against the reference's own (f64 batch sums here, f32 / f64 numpy sums there)
+        np.testing.assert_allclose([st["epi_mean"], st["epi_var"], st["epi_count"]], g["epi_rms"][t], rtol=1e-5)
+        np.testing.assert_allclose([st["intr_mean"], st["intr_var"], st["intr_count"]], g["intr_rms"][t], rtol=1e-5)
         eng.reset_host(g["done"][t])
     st = eng.get_state()
     assert st["cursor"] == int(g["cursor_final"])

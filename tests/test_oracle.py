@@ -30,6 +30,11 @@ def test_oracle_matches_reference_golden(name, use_c):
         np.testing.assert_allclose(orc.ed_rms.mean, g["mean"][t], rtol=1e-6)
         np.testing.assert_allclose(orc.ed_rms.var, g["var"][t], rtol=1e-4, atol=1e-9)
         assert float(orc.ed_rms.count) == g["count"][t]
+        # log-only trackers (episodic_novelty.py:82, intrinsic_novelty.py:32): the oracle's rewards differ from
+        # the reference's by torch's non-correctly-rounded CPU sqrt (<= 3e-7), so do the statistics
+        np.testing.assert_allclose(orc.epi_novel_rms.triple(), g["epi_rms"][t], rtol=2e-6)
+        np.testing.assert_allclose(orc.intrinsic_novel_rms.triple(), g["intr_rms"][t], rtol=2e-6)
+        assert orc.epi_novel_rms.triple()[2] == g["epi_rms"][t][2] and orc.intrinsic_novel_rms.triple()[2] == g["intr_rms"][t][2]
         orc.reset(g["done"][t])
     assert orc.cursor == int(g["cursor_final"])
     if g["mem_final"].size:
