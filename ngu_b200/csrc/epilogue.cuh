@@ -294,8 +294,8 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // next step's scan may start its prologue
 
     // While the scan is still streaming: pull this kernel's small inputs into L2 (the scan's TMA
-    // traffic is tagged evict-first, so they stay there).  L2 is the coherence point, so
-    // prefetching lines that the previous epilogue may still be writing is harmless.
+    // traffic is tagged evict-first, so they stay there).  The previous epilogue has completed by now
+    // (the scan signals launch_dependents after its own griddepcontrol.wait).
     if (threadIdx.x < 5) prefetch_l2(reinterpret_cast<const char*>(st) + 128 * threadIdx.x);
     if (threadIdx.x == 5) prefetch_l2(p.plan);
     if (append && !p.stage_q)
