@@ -268,6 +268,32 @@ def run_gpu_arm(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = B * world * K / float(t.item())
 
+    stream_only_ms = None
+    if rank == 0 and not args.no_stream_only:
+        # Diagnostic: the SAME scan kernel with its arithmetic, top-k and flushes switched off (results invalid),
+        # on a second memory of the same size: what this TMA access pattern alone takes on this box.
+        # Kept out of every reported throughput.
+        try:
+            from ngu_b200.engine import EpisodicEngine
+            os.environ["NGU_EPI_DEBUG_SCAN"] = "15"
+            try:
+                bare = EpisodicEngine(B, N, device=local_rank, k=K_NEIGHBORS, scan_variant=args.scan_variant)
+            finally:
+                del os.environ["NGU_EPI_DEBUG_SCAN"]
+            bare._memory.normal_(generator=g)
+            for i in range(30):
+                bare.scan(qs[i % NQ])
+            torch.cuda.synchronize()
+            bare.scan_timing_begin(100)
+            for i in range(100):
+                bare.scan(qs[i % NQ])
+            ms, n = bare.scan_timing_end()
+            stream_only_ms = ms / max(n, 1)
+            bare.close()
+            del bare
+        except Exception as e:                      # a diagnostic must never cost the bench line
+            print(f"stream-only diagnostic skipped: {e}", file=sys.stderr)
+
     if rank == 0:
         peak, peak_src = measured_peak()
         scan_avg_ms = scan_ms / max(scan_calls, 1)
@@ -296,7 +322,10 @@ def run_gpu_arm(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                          "peak_source": peak_src, "launch_ms": scan_avg_ms,
-                         "algorithmic_bytes_per_launch": BYTES_PER_QUERY_FOR(N) * B},
+                         "algorithmic_bytes_per_launch": BYTES_PER_QUERY_FOR(N) * B,
+                         "stream_only_launch_ms": stream_only_ms,
+                         "stream_only_note": "same kernel, distance math / top-k / flush / merge switched off "
+                                             "(NGU_EPI_DEBUG_SCAN=15): the TMA stream alone, live on this box"},
         }
         if world == 1 and not args.no_cpu_baseline:
             qps, ms, done, threads = cpu_reference_run(B, N, 30, 1, time_budget_s=12)
@@ -323,6 +352,7 @@ def main():
     ap.add_argument("--capacity", type=int, default=CAPACITY)
     ap.add_argument("--scan-variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stream-only", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", 0))
