@@ -16,6 +16,15 @@
  *     legacy default stream).  Calls that take a stream only enqueue work and
  *     return without synchronising; *_host calls are synchronous;
  *   - one handle per GPU / per shard of actors; a handle is not thread-safe;
+ *   - every call runs on the handle's GPU and restores the caller's current CUDA device on return;
+ *   - stream contract: *_host calls run on a private non-blocking stream of the handle.  They are
+ *     ordered after whatever the caller enqueued THROUGH THIS HANDLE on the stream it last passed
+ *     (append, device-mask reset, device-pointer steps).  Work enqueued on a stream by other means
+ *     (e.g. a torch copy into the memory view) must be synchronised by the caller first;
+ *   - sticky error: the k-NN merge and the multi-GPU exchange wait for data with a (generous) time
+ *     budget.  If one ever gives up, the results would be silently wrong, so the library fails loudly
+ *     instead: ngu_epi_state.exchange_timeouts becomes non-zero and stays so, every reward produced
+ *     from then on is NaN, and ngu_epi_scan / _finish / _step* return NGU_ESTATE.  Recreate the handle;
  *   - there is no CPU fallback: without a CUDA device every call fails.
  *
  * Data layout in HBM (owned by the handle unless `memory_dev` is supplied):
@@ -34,7 +43,7 @@
 extern "C" {
 #endif
 
-#define NGU_EPI_ABI_VERSION 3
+#define NGU_EPI_ABI_VERSION 4
 #define NGU_EPI_DIM 32          /* controllable_state_dim, episodic_novelty.py:23 */
 #define NGU_EPI_MAX_K 32        /* k-NN list lives in one warp */
 
@@ -43,7 +52,7 @@ enum {
     NGU_EINVAL = -1,            /* bad argument / unsupported configuration */
     NGU_ECUDA = -2,             /* a CUDA runtime / driver call failed */
     NGU_ENOMEM = -3,
-    NGU_ESTATE = -4             /* call order violated (e.g. finish before scan) */
+    NGU_ESTATE = -4             /* call order violated (e.g. finish before scan), or the sticky error above */
 };
 
 enum {
@@ -87,7 +96,8 @@ typedef struct ngu_epi_state {
     double intr_mean, intr_var, intr_count;
     int64_t cursor;
     int64_t steps;              /* finished steps since create / set_state */
-    int64_t exchange_timeouts;  /* read-only: p2p exchange rounds that timed out waiting for a peer (0 = healthy) */
+    int64_t exchange_timeouts;  /* read-only, sticky: k-NN merges / p2p exchange rounds that gave up waiting (0 = healthy);
+                                   ngu_epi_set_state ignores it */
     double ll_mean, ll_var, ll_count;   /* LifelongNovelty.ll_rms (lifelong_novelty.py:26), used by ngu_epi_step_rnd */
 } ngu_epi_state;
 
@@ -150,10 +160,14 @@ int ngu_epi_append(ngu_epi* h, const float* q_dev, void* stream);
  * zero every slot of each actor b with done_dev[b] != 0; cursor untouched. */
 int ngu_epi_reset(ngu_epi* h, const uint8_t* done_dev, void* stream);
 
-/* Single-shard convenience = scan -> finish (own sums) -> log_update -> append,
- * i.e. one call of EpisodicNovelty.compute_episodic_novelty followed by the
- * multiplier of IntrinsicNovelty.compute_intrinsic_novelty
- * (episodic_novelty.py:37-84, intrinsic_novelty.py:20-34), all on `stream`. */
+/* One whole step in two launches: the scan kernel (distance scan + top-k + merge), then ONE epilogue
+ * kernel = rank sums -> [p2p exchange over NVLink when connected, see below] -> running-mean update ->
+ * rewards x clip(alpha, 1, L) -> append; the log-only trackers absorb the step's rewards at the start of
+ * the NEXT fused launch (or on ngu_epi_get_state / ngu_epi_log_flush).  I.e. one call of
+ * EpisodicNovelty.compute_episodic_novelty followed by the multiplier of
+ * IntrinsicNovelty.compute_intrinsic_novelty (episodic_novelty.py:37-84, intrinsic_novelty.py:20-34),
+ * all on `stream`.  r_int is float32: the reference's product of a float32 reward and numpy's float64
+ * alpha is float64 under numpy >= 2 (intrinsic_novelty.py:31); the values agree to float32 rounding. */
 int ngu_epi_step(ngu_epi* h, const float* q_dev, const float* alpha_dev,
                  float* r_int_dev, float* r_epi_dev, void* stream);
 
@@ -187,9 +201,16 @@ int ngu_epi_topk_host(ngu_epi* h, float* d2_host, int32_t* idx_host);
  * the hot path) are kept off the step's critical path: a fused step (ngu_epi_step*, ngu_epi_step_host)
  * stashes its rewards on the device and the next fused step folds them in while its scan runs.
  * ngu_epi_get_state folds an outstanding stash in first, so what it returns is always up to date
- * (single GPU; connected ranks call ngu_epi_log_flush first, below).  ngu_epi_set_state drops it. */
+ * (single GPU; connected ranks call ngu_epi_log_flush first, below).
+ * ngu_epi_set_state replaces the PUBLIC fields only (an outstanding stash is folded in first, i.e. into the
+ * values being replaced).  The library's bookkeeping - log-only sums waiting for the next exchange round, the
+ * exchange sequence numbers, the sticky exchange_timeouts counter - is never touched, so a get/modify/set
+ * round trip loses nothing and a set_state on one rank cannot desynchronise the exchange.  With connected
+ * ranks the public fields are replicated state: set the same values on every rank.
+ * ngu_epi_set_cursor moves only the ring cursor (EpisodicNovelty.memory_idx, episodic_novelty.py:34). */
 int ngu_epi_get_state(ngu_epi* h, ngu_epi_state* out);
 int ngu_epi_set_state(ngu_epi* h, const ngu_epi_state* in);
+int ngu_epi_set_cursor(ngu_epi* h, int64_t cursor);
 
 /* Bulk load / dump of the episodic memory in the REFERENCE layout
  * float[capacity][n_actors][32] on the host (tests, checkpoints).  Synchronous. */
@@ -221,6 +242,9 @@ int ngu_epi_scan_geometry(const ngu_epi* h, int32_t out[8]);
  * schedule, in units of tiles of tile_rows memory slots over the linear space actor * tiles_per_actor +
  * tile; the ranges of all chunks partition that space (tests/test_gpu_parity.py). */
 int ngu_epi_debug_chunk(const ngu_epi* h, int32_t idx, int32_t out[2]);
+/* Test aid: make the handle look as if a merge / exchange round had timed out (sets the sticky counter on the
+ * device), so that the failure path can be exercised: NaN rewards, NGU_ESTATE from the next step. */
+int ngu_epi_debug_inject_timeout(ngu_epi* h);
 /* The same plan WITHOUT a handle or a GPU (host logic only; the CPU test suite checks the partition for
  * many shapes): geo[8] as ngu_epi_scan_geometry for a device with `sm_count` SMs; chunks (may be NULL)
  * receives 2 * geo[7] ints, [first tile, end tile) per chunk; max_chunks = capacity of `chunks` in chunks. */

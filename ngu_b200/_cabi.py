@@ -14,6 +14,7 @@ from .build import LIB_PATH
 MAX_K = 32
 DIM = 32
 MODE_REFERENCE, MODE_PAPER = 0, 1
+ABI_VERSION = 4
 
 
 class NguEpiCfg(C.Structure):
@@ -58,6 +59,7 @@ SYMBOLS = {
     "ngu_epi_topk_host": (C.c_int, [_P, _P, _P]),
     "ngu_epi_get_state": (C.c_int, [_P, C.POINTER(NguEpiState)]),
     "ngu_epi_set_state": (C.c_int, [_P, C.POINTER(NguEpiState)]),
+    "ngu_epi_set_cursor": (C.c_int, [_P, C.c_int64]),
     "ngu_epi_load_memory_host": (C.c_int, [_P, _P]),
     "ngu_epi_dump_memory_host": (C.c_int, [_P, _P]),
     "ngu_epi_p2p_export": (C.c_int, [_P, _P, C.c_int32]),
@@ -66,6 +68,7 @@ SYMBOLS = {
     "ngu_epi_launch_count": (C.c_int64, [_P]),
     "ngu_epi_scan_geometry": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "ngu_epi_debug_chunk": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32)]),
+    "ngu_epi_debug_inject_timeout": (C.c_int, [_P]),
     "ngu_epi_plan_host": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), _P, C.c_int32]),
     "ngu_epi_debug_timeline": (C.c_int, [_P, _P, C.c_int32]),
     "ngu_epi_scan_timing_begin": (C.c_int, [_P, C.c_int32]),
@@ -93,7 +96,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the ABI is out of date
         fn.restype = res
         fn.argtypes = args
-    if lib.ngu_epi_abi_version() != 3:
+    if lib.ngu_epi_abi_version() != ABI_VERSION:
         raise NguEpiError("libngu_epi.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

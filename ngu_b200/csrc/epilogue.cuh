@@ -25,14 +25,21 @@ struct DevState {
     double ed_count;
     double epi_mean, epi_var, epi_count;
     double intr_mean, intr_var, intr_count;
-    long long steps;     // the 16 words from ed_count to pending_log are staged together by the epilogue
+    long long steps;     // the kStagedWords words from ed_count to stash_open are staged together by the epilogue
     double ll_mean, ll_var, ll_count;   // LifelongNovelty.ll_rms (lifelong_novelty.py:26,54), RND fused path only
+    // ---- internal from here on: ngu_epi_set_state never touches these ----
     double pending_log[5];              // p2p mode: this shard's log-only sums of the last step, not yet exchanged
-    long long flush_seq;                // sequence number of on-demand log flush rounds
-    long long cursor;
-    long long exchange_timeouts;   // p2p exchange rounds that gave up waiting for a peer (must stay 0)
+    long long xchg_seq;                 // p2p mode: sequence number (tag) of the next per-step exchange round; NOT the public
+                                        // `steps`, so that a set_state on one rank cannot desynchronise the tags
+    long long cursor;                   // (public, but staged with the block)
+    long long exchange_timeouts;   // merges / p2p exchange rounds that gave up waiting (must stay 0; sticky error, see below)
     long long stash_open;          // 1: log_stash holds the rewards of a fused step not yet folded into the trackers
+    long long flush_seq;                // sequence number of on-demand log flush rounds
 };
+constexpr int kStagedWords = 20;   // ed_count .. stash_open
+// indices into the staged block
+enum : int { SC_ED_COUNT = 0, SC_EPI = 1, SC_INTR = 4, SC_STEPS = 7, SC_LL = 8, SC_PENDING = 11, SC_XCHG_SEQ = 16, SC_CURSOR = 17,
+             SC_TIMEOUTS = 18, SC_STASH_OPEN = 19 };
 
 struct EpiConsts {
     float eps, cluster, pseudo, s_max, max_rew;
@@ -146,6 +153,7 @@ struct EpilogueParams {
     float* alpha_out;         // [B] or null: the modulator computed by the RND phase
     P2PView p2p;              // used when phases & PH_EXCHANGE
     float* log_stash;         // [2][B] r_epi, r_int of the last fused step (PH_LOGFUSE), see log_absorb
+    unsigned int* host_err;   // mapped host word: set to 1 when a merge / exchange timed out (sticky error, never cleared)
     unsigned int* host_flag;  // mapped host word or null: receives host_seq after the kernel's last write
     unsigned int host_seq;
     unsigned long long* dbg_stamps;   // debug (NGU_EPI_DEBUG_EPILOGUE=1): %globaltimer at phase boundaries, thread 0
@@ -154,10 +162,13 @@ struct EpilogueParams {
 // Chan/Welford merge of (mean, var, count) with a batch (mpi_util.py:59-73), all f64.
 __device__ __noinline__ void rms_merge(double* mean, double* var, double* count, double b_mean, double b_var,
                                        double b_count) {
-    const double delta = b_mean - *mean;
-    const double tot = *count + b_count;
-    const double m2 = *var * *count + b_var * b_count + f64_div(delta * delta * *count * b_count, tot);
-    *mean = *mean + f64_div(delta * b_count, tot);
+    // every product and sum separately rounded (numpy does not contract): no FMA
+    const double delta = __dsub_rn(b_mean, *mean);
+    const double tot = __dadd_rn(*count, b_count);
+    const double m_a = __dmul_rn(*var, *count), m_b = __dmul_rn(b_var, b_count);
+    const double cross = f64_div(__dmul_rn(__dmul_rn(__dmul_rn(delta, delta), *count), b_count), tot);
+    const double m2 = __dadd_rn(__dadd_rn(m_a, m_b), cross);
+    *mean = __dadd_rn(*mean, f64_div(__dmul_rn(delta, b_count), tot));
     *var = f64_div(m2, tot);
     *count = tot;
 }
@@ -166,9 +177,9 @@ __device__ __noinline__ void rms_merge(double* mean, double* var, double* count,
 __device__ __noinline__ void log_rms_apply(double* sc, const double* ls) {
     const double n = ls[4];
     if (n > 0.0) {
-        const double m1 = f64_div(ls[0], n), v1 = fmax(f64_div(ls[1], n) - m1 * m1, 0.0);
+        const double m1 = f64_div(ls[0], n), v1 = fmax(__dsub_rn(f64_div(ls[1], n), __dmul_rn(m1, m1)), 0.0);
         rms_merge(&sc[0], &sc[1], &sc[2], m1, v1, n);
-        const double m2 = f64_div(ls[2], n), v2 = fmax(f64_div(ls[3], n) - m2 * m2, 0.0);
+        const double m2 = f64_div(ls[2], n), v2 = fmax(__dsub_rn(f64_div(ls[3], n), __dmul_rn(m2, m2)), 0.0);
         rms_merge(&sc[3], &sc[4], &sc[5], m2, v2, n);
     }
 }
@@ -180,7 +191,7 @@ __device__ __forceinline__ void apply_log_sums(DevState* st, double* s_scal, con
     const double n = ls[4];
     if (n > 0.0) {
         const int o = 2 * which;
-        const double m = f64_div(ls[o], n), v = fmax(f64_div(ls[o + 1], n) - m * m, 0.0);
+        const double m = f64_div(ls[o], n), v = fmax(__dsub_rn(f64_div(ls[o + 1], n), __dmul_rn(m, m)), 0.0);
         double* sc = s_scal + 1 + 3 * which;
         rms_merge(&sc[0], &sc[1], &sc[2], m, v, n);
         for (int q = 0; q < 3; ++q) (&st->ed_count)[1 + 3 * which + q] = sc[q];
@@ -270,7 +281,8 @@ template <int THREADS>   // THREADS >= 8 * NGU_EPI_MAX_K (8 lanes per column in 
 __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams p, const EpiConsts c) {
     __shared__ double s_sums[2 * 32 + 1 + 5 + 2];   // rank sums (+ piggybacked log sums in p2p mode)
     __shared__ double s_mean[32], s_var[32];
-    __shared__ double s_scal[16];     // ed_count, epi(mean,var,count), intr(mean,var,count), steps, ll(mean,var,count), pending_log[5]
+    __shared__ double s_scal[kStagedWords];   // DevState from ed_count on: see the SC_* indices
+    __shared__ int s_failed;                  // this launch saw (or inherited) a timed-out merge / exchange: rewards become NaN
     __shared__ double s_recv[kMaxWorld * 72];   // p2p receive scratch
     __shared__ double s_ll[2];
     __shared__ float mean32[32];
@@ -292,6 +304,7 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
 #define EPI_STAMP(i) do { if (p.dbg_stamps && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg_stamps[i] = t_; } } while (0)
     EPI_STAMP(8);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // next step's scan may start its prologue
+    if (threadIdx.x == 0) s_failed = 0;   // (read after the load phase's barrier at the earliest)
 
     // While the scan is still streaming: pull this kernel's small inputs into L2 (the scan's TMA
     // traffic is tagged evict-first, so they stay there).  The previous epilogue has completed by now
@@ -369,15 +382,16 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
             s_mean[threadIdx.x] = __ldcg(&st->ed_mean[threadIdx.x]);
             s_var[threadIdx.x] = __ldcg(&st->ed_var[threadIdx.x]);
         }
-        if (threadIdx.x >= 32 && threadIdx.x < 48) s_scal[threadIdx.x - 32] = __ldcg(&st->ed_count + (threadIdx.x - 32));
     }
-    if (append) {
-        if (threadIdx.x == 64) s_cursor = __ldcg(&st->cursor);
-    }
+    // staged even without FINISH: cursor (APPEND) and the sticky timeout counter live in the block
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + kStagedWords) s_scal[threadIdx.x - 32] = __ldcg(&st->ed_count + (threadIdx.x - 32));
 #pragma unroll 1
     for (int i = threadIdx.x; i < p.plan_len + p.n_leaves; i += THREADS) s_plan[i] = __ldcg(p.plan + i);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
+    // Sticky error (include/ngu_epi.h): a merge of this or an earlier scan, or an earlier exchange, gave up waiting.
+    // Whatever would be computed from here on is wrong, so say so loudly: NaN rewards and the mapped error word.
+    const bool failed_before = __double_as_longlong(s_scal[SC_TIMEOUTS]) != 0;
     EPI_STAMP(1);
 
     if (rnd) {
@@ -403,7 +417,7 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
                 const float b_var = __fmul_rn(b_std, b_std);                       // np.square(batch_std)
                 const double m_b = static_cast<double>(__fmul_rn(b_var, nB));      // batch_var * batch_count stays f32
                 const double n_b = static_cast<double>(B);
-                const double mean = s_scal[8], var = s_scal[9], count = s_scal[10];
+                const double mean = s_scal[SC_LL], var = s_scal[SC_LL + 1], count = s_scal[SC_LL + 2];
                 const double delta = static_cast<double>(bmean) - mean;
                 const double totc = count + n_b;
                 const double new_mean = mean + f64_div(delta * n_b, totc);
@@ -486,11 +500,14 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
         // sums of the PREVIOUS step (episodic_novelty.py:82, intrinsic_novelty.py:32) - the trackers they
         // feed are never read by the hot path, so they are brought up to date one step late (or on
         // demand: ngu_epi_log_flush) instead of paying a second rendezvous per step.
-        const unsigned long long step_id = static_cast<unsigned long long>(__double_as_longlong(s_scal[7]));
-        if (threadIdx.x < 5) s_sums[2 * k + 1 + threadIdx.x] = s_scal[11 + threadIdx.x];
+        const unsigned long long xseq = static_cast<unsigned long long>(__double_as_longlong(s_scal[SC_XCHG_SEQ]));
+        if (threadIdx.x < 5) s_sums[2 * k + 1 + threadIdx.x] = s_scal[SC_PENDING + threadIdx.x];
         __syncthreads();
-        if (!p2p_allreduce<THREADS>(p.p2p, s_sums, 2 * k + 6, 0, step_id, s_recv) && threadIdx.x == 0)
+        if (!p2p_allreduce<THREADS>(p.p2p, s_sums, 2 * k + 6, 0, xseq, s_recv) && threadIdx.x == 0) {
             atomicAdd(reinterpret_cast<unsigned long long*>(&st->exchange_timeouts), 1ull);
+            s_failed = 1;
+        }
+        if (threadIdx.x == 32) st->xchg_seq = static_cast<long long>(xseq + 1ull);
         if (threadIdx.x < 2) apply_log_sums(st, s_scal, s_sums + 2 * k + 1, threadIdx.x);
         __syncthreads();
     }
@@ -507,7 +524,7 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
             // mpi_mean: globalsum[:n] / globalsum[n] in float32 (mpi_util.py:18)
             const float b_mean = f32_div(static_cast<float>(s_sums[j]), cnt32);
             const double bm = static_cast<double>(b_mean);
-            const double count = s_scal[0];
+            const double count = s_scal[SC_ED_COUNT];
             const double n_b = static_cast<double>(cnt32);
             const double delta = bm - s_mean[j];
             const double totc = count + n_b;
@@ -528,8 +545,8 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
             }
         }
         if (threadIdx.x == 64) {
-            st->ed_count = s_scal[0] + static_cast<double>(static_cast<float>(s_sums[2 * k]));
-            st->steps = st_steps_plus_one(s_scal[7]);
+            st->ed_count = s_scal[SC_ED_COUNT] + static_cast<double>(static_cast<float>(s_sums[2 * k]));
+            st->steps = st_steps_plus_one(s_scal[SC_STEPS]);
         }
         __syncthreads();
         EPI_STAMP(4);
@@ -546,6 +563,7 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
         }
         __syncthreads();
         // (ii) one thread per actor
+        const bool failed = failed_before || s_failed != 0;
         double acc4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
         for (int b = threadIdx.x; b < B; b += THREADS) {
@@ -558,7 +576,8 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
             float a = s_alpha[b];
             if (a < 1.0f) a = 1.0f;                                                 // intrinsic_novelty.py:26-27
             if (a > c.max_rew) a = c.max_rew;                                       // :28-29
-            const float ri = __fmul_rn(r, a);                                       // :31
+            float ri = __fmul_rn(r, a);                                             // :31
+            if (failed) { r = __int_as_float(0x7fc00000); ri = r; }                 // sticky error: never a plausible number
             if (p.r_epi) p.r_epi[b] = r;
             p.r_int[b] = ri;
             if (logfuse) {       // log-only statistics: stashed, absorbed by the next launch (log_absorb)
@@ -579,7 +598,7 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
 
     EPI_STAMP(6);
     if (append) {
-        const long long cur = s_cursor;
+        const long long cur = __double_as_longlong(s_scal[SC_CURSOR]);
         const float4* q4 = reinterpret_cast<const float4*>(p.q);
 #pragma unroll 1
         for (int i = threadIdx.x; i < B * 8; i += THREADS) {
@@ -591,6 +610,7 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
     }
 
     EPI_STAMP(7);
+    if (threadIdx.x == 0 && p.host_err && (failed_before || s_failed != 0)) *reinterpret_cast<volatile unsigned int*>(p.host_err) = 1u;
     if (p.host_flag) {   // ngu_epi_step_host: tell the spinning host that every write of the step has been issued
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -613,7 +633,7 @@ __global__ void __launch_bounds__(kLogThreads) log_absorb_kernel(DevState* st, c
 }
 
 __global__ void __launch_bounds__(kLogThreads) log_flush_kernel(DevState* st, P2PView v, const float* stash, int B) {
-    __shared__ double s_scal[16];
+    __shared__ double s_scal[kStagedWords];
     __shared__ double s_vals[8];
     __shared__ double s_recv[kMaxWorld * 8];
     __shared__ double red[4][kLogThreads / 32];
@@ -621,9 +641,9 @@ __global__ void __launch_bounds__(kLogThreads) log_flush_kernel(DevState* st, P2
     if (__ldcg(&st->stash_open) != 0)                      // CTA-uniform
         log_absorb<kLogThreads>(st, stash, B, true, red, s_log);
     __syncthreads();
-    if (threadIdx.x < 16) s_scal[threadIdx.x] = __ldcg(&st->ed_count + threadIdx.x);
+    if (threadIdx.x < kStagedWords) s_scal[threadIdx.x] = __ldcg(&st->ed_count + threadIdx.x);
     __syncthreads();
-    if (threadIdx.x < 5) s_vals[threadIdx.x] = s_scal[11 + threadIdx.x];
+    if (threadIdx.x < 5) s_vals[threadIdx.x] = s_scal[SC_PENDING + threadIdx.x];
     __syncthreads();
     const unsigned long long seq = static_cast<unsigned long long>(st->flush_seq);
     if (!p2p_allreduce<kLogThreads>(v, s_vals, 5, kFlushElem, seq, s_recv) && threadIdx.x == 0)

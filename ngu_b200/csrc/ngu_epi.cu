@@ -139,6 +139,11 @@ struct ngu_epi {
     // but the GPU side starts later and loses more (wait 162 -> 174 us at 256 x 30k).
     unsigned int* flag_mapped = nullptr;
     unsigned int* flag_mapped_dev = nullptr;
+    unsigned int* err_mapped = nullptr;       // = flag_mapped + 8: sticky error word written by the epilogue (check_sticky)
+    unsigned int* err_mapped_dev = nullptr;
+    cudaStream_t user_stream = nullptr;       // last stream the caller passed to a stream-taking entry point
+    bool user_stream_dirty = false;           // ... and it may still hold work the *_host calls must be ordered after
+    cudaEvent_t order_ev = nullptr;
     unsigned int host_seq = 0;
     bool host_flag_wait = true;      // experiments: NGU_EPI_HOST_PATH=sync -> stream synchronize instead
     bool host_profile = false;       // NGU_EPI_HOST_PROFILE=1: wall-clock split of ngu_epi_step_host, printed at destroy
@@ -170,8 +175,39 @@ int fail(ngu_epi* h, int code, const std::string& msg) {
             return fail(h, NGU_ECUDA, fmt("%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__)); \
     } while (0)
 
-int bind_device(ngu_epi* h) {
-    CU_TRY(h, cudaSetDevice(h->cfg.device));
+// Every entry point runs on the handle's GPU and leaves the caller's current device as it found it
+// (a handle on cuda:1 must not silently switch a thread whose torch current device is cuda:0).
+struct DeviceGuard {
+    int prev = -1, rc = NGU_OK;
+    explicit DeviceGuard(ngu_epi* h) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e == cudaSuccess && prev != h->cfg.device) e = cudaSetDevice(h->cfg.device); else if (e == cudaSuccess) prev = -1;
+        if (e != cudaSuccess) { prev = -1; rc = fail(h, NGU_ECUDA, fmt("cudaSetDevice(%d): %s", h->cfg.device, cudaGetErrorString(e))); }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define BIND_DEVICE(h) DeviceGuard dev_guard_(h); if (dev_guard_.rc) return dev_guard_.rc
+
+// Sticky error: once a merge or an exchange round has timed out (DevState::exchange_timeouts != 0, mirrored by
+// the epilogue into a mapped host word) every later result is wrong - the step entry points refuse to go on.
+int check_sticky(ngu_epi* h) {
+    if (h->err_mapped && *reinterpret_cast<volatile unsigned int*>(h->err_mapped) != 0u)
+        return fail(h, NGU_ESTATE, "a k-NN merge or a p2p exchange round timed out earlier (ngu_epi_state.exchange_timeouts != 0): "
+                                   "rewards since then are NaN and the replicated statistics may have diverged; recreate the handle");
+    return NGU_OK;
+}
+
+// *_host calls run on the handle's private stream.  Work the caller enqueued through this handle on ITS stream
+// (append, device-mask reset, device-pointer steps) must be ordered before them: remember that stream and make
+// the private stream wait for it at the next *_host entry.
+void note_user_stream(ngu_epi* h, cudaStream_t s) { h->user_stream = s; h->user_stream_dirty = true; }
+int order_after_user_stream(ngu_epi* h) {
+    if (!h->user_stream_dirty) return NGU_OK;
+    CU_TRY(h, cudaEventRecord(h->order_ev, h->user_stream));
+    CU_TRY(h, cudaStreamWaitEvent(h->own_stream, h->order_ev, 0));
+    h->user_stream_dirty = false;
     return NGU_OK;
 }
 
@@ -426,6 +462,9 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
     CREATE_TRY(cudaHostAlloc(&h->flag_mapped, 64, cudaHostAllocMapped));
     CREATE_TRY(cudaHostGetDevicePointer(&h->flag_mapped_dev, h->flag_mapped, 0));
     *h->flag_mapped = 0u;
+    h->err_mapped = h->flag_mapped + 8; h->err_mapped_dev = h->flag_mapped_dev + 8;
+    *h->err_mapped = 0u;
+    CREATE_TRY(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
 
     if (const char* e = getenv("NGU_EPI_HOST_PATH")) h->host_flag_wait = std::strcmp(e, "sync") != 0;
     if (const char* e = getenv("NGU_EPI_HOST_PROFILE")) h->host_profile = atoi(e) != 0;
@@ -455,10 +494,11 @@ void ngu_epi_destroy(ngu_epi* h) {
         fprintf(stderr, "[ngu_epi] step_host x%ld: stage-in %.2f us, enqueue %.2f us, wait %.2f us, copy-out %.2f us per call\n",
                 h->prof_calls, h->prof_us[0] / h->prof_calls, h->prof_us[1] / h->prof_calls, h->prof_us[2] / h->prof_calls,
                 h->prof_us[3] / h->prof_calls);
-    cudaSetDevice(h->cfg.device);
+    DeviceGuard dev_guard_(h);
     if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
     for (cudaEvent_t e : h->t_beg) cudaEventDestroy(e);
     for (cudaEvent_t e : h->t_end) cudaEventDestroy(e);
+    if (h->order_ev) cudaEventDestroy(h->order_ev);
     if (h->p2p_connected)
         for (int g = 0; g < h->p2p.world; ++g)
             if (g != h->p2p.rank && h->p2p.peer[g]) cudaIpcCloseMemHandle(h->p2p.peer[g]);
@@ -530,6 +570,7 @@ static int launch_epilogue(ngu_epi* h, int phases, const double* sums_in, const 
                            const RndArgs* rnd = nullptr, const HostFlag* hf = nullptr) {
     EpilogueParams ep{};
     if (hf) { ep.host_flag = hf->flag; ep.host_seq = hf->seq; }
+    ep.host_err = h->err_mapped_dev;
     ep.dbg_stamps = h->epi_stamps;
     if (rnd) { ep.rnd_pred = rnd->pred; ep.rnd_targ = rnd->targ; ep.alpha_out = rnd->alpha_out; }
     ep.dist = h->dist; ep.rank_sums = h->rank_sums; ep.sums_in = sums_in; ep.alpha = alpha;
@@ -553,9 +594,11 @@ static int launch_epilogue(ngu_epi* h, int phases, const double* sums_in, const 
 
 int ngu_epi_scan(ngu_epi* h, const float* q_dev, void* stream) {
     if (!h || !q_dev) return fail(h, NGU_EINVAL, "null argument");
-    int rc = bind_device(h);
+    BIND_DEVICE(h);
+    int rc = check_sticky(h);
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    note_user_stream(h, s);
     rc = launch_scan(h, q_dev, s);
     if (rc) return rc;
     rc = launch_epilogue(h, PH_RANKSUMS, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, s);
@@ -573,9 +616,11 @@ int ngu_epi_rank_sums(ngu_epi* h, double** sums_dev) {
 int ngu_epi_finish(ngu_epi* h, const double* sums_global_dev, const float* alpha_dev, float* r_int_dev,
                    float* r_epi_dev, double* log_sums_dev, void* stream) {
     if (!h || !r_int_dev) return fail(h, NGU_EINVAL, "null argument");
-    int rc = bind_device(h);
+    BIND_DEVICE(h);
+    int rc = check_sticky(h);
     if (rc) return rc;
     if (!h->scanned) return fail(h, NGU_ESTATE, "ngu_epi_finish called before ngu_epi_scan");
+    note_user_stream(h, static_cast<cudaStream_t>(stream));
     rc = launch_epilogue(h, PH_FINISH, sums_global_dev ? sums_global_dev : h->rank_sums, alpha_dev, r_int_dev,
                          r_epi_dev, log_sums_dev, nullptr, static_cast<cudaStream_t>(stream));
     if (rc) return rc;
@@ -585,8 +630,8 @@ int ngu_epi_finish(ngu_epi* h, const double* sums_global_dev, const float* alpha
 
 int ngu_epi_log_update(ngu_epi* h, const double* log_sums_global_dev, void* stream) {
     if (!h || !log_sums_global_dev) return fail(h, NGU_EINVAL, "null argument");
-    int rc = bind_device(h);
-    if (rc) return rc;
+    BIND_DEVICE(h);
+    note_user_stream(h, static_cast<cudaStream_t>(stream));
     log_update_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(h->state, log_sums_global_dev);
     CU_TRY(h, cudaGetLastError());
     h->launches += 1;
@@ -595,8 +640,8 @@ int ngu_epi_log_update(ngu_epi* h, const double* log_sums_global_dev, void* stre
 
 int ngu_epi_append(ngu_epi* h, const float* q_dev, void* stream) {
     if (!h || !q_dev) return fail(h, NGU_EINVAL, "null argument");
-    int rc = bind_device(h);
-    if (rc) return rc;
+    BIND_DEVICE(h);
+    note_user_stream(h, static_cast<cudaStream_t>(stream));
     append_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(h->memory, q_dev, h->state, h->cfg.n_actors,
                                                                     h->cfg.capacity);
     CU_TRY(h, cudaGetLastError());
@@ -606,8 +651,8 @@ int ngu_epi_append(ngu_epi* h, const float* q_dev, void* stream) {
 
 int ngu_epi_reset(ngu_epi* h, const uint8_t* done_dev, void* stream) {
     if (!h || !done_dev) return fail(h, NGU_EINVAL, "null argument");
-    int rc = bind_device(h);
-    if (rc) return rc;
+    BIND_DEVICE(h);
+    if (static_cast<cudaStream_t>(stream) != h->own_stream) note_user_stream(h, static_cast<cudaStream_t>(stream));
     const int64_t n4 = static_cast<int64_t>(h->cfg.capacity) * 8;
     dim3 grid(static_cast<unsigned>((n4 + 2047) / 2048), h->cfg.n_actors < kResetGroups ? h->cfg.n_actors : kResetGroups);
     reset_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->memory, done_dev, h->cfg.n_actors, h->cfg.capacity);
@@ -629,8 +674,10 @@ static int step_impl(ngu_epi* h, const float* q_dev, const float* alpha_dev, flo
 int ngu_epi_step(ngu_epi* h, const float* q_dev, const float* alpha_dev, float* r_int_dev, float* r_epi_dev,
                  void* stream) {
     if (!h || !q_dev || !r_int_dev) return fail(h, NGU_EINVAL, "null argument");
-    int rc = bind_device(h);
+    BIND_DEVICE(h);
+    const int rc = check_sticky(h);
     if (rc) return rc;
+    note_user_stream(h, static_cast<cudaStream_t>(stream));
     return step_impl(h, q_dev, alpha_dev, r_int_dev, r_epi_dev, static_cast<cudaStream_t>(stream), nullptr);
 }
 
@@ -638,9 +685,11 @@ int ngu_epi_step_rnd(ngu_epi* h, const float* q_dev, const float* pred_dev, cons
                      float* r_int_dev, float* r_epi_dev, float* alpha_out_dev, void* stream) {
     if (!h || !q_dev || !pred_dev || !targ_dev || !r_int_dev) return fail(h, NGU_EINVAL, "null argument");
     if (feat_dim != 128) return fail(h, NGU_EINVAL, "the RND feature width must be 128 (rnd_prediction.py:27)");
-    int rc = bind_device(h);
+    BIND_DEVICE(h);
+    int rc = check_sticky(h);
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    note_user_stream(h, s);
     rc = launch_scan(h, q_dev, s);
     if (rc) return rc;
     RndArgs ra{pred_dev, targ_dev, alpha_out_dev};
@@ -669,7 +718,10 @@ static int wait_host_flag(ngu_epi* h, unsigned int seq, cudaStream_t s) {
 int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host, float* r_int_host,
                       float* r_epi_host) {
     if (!h || !q_host || !r_int_host) return fail(h, NGU_EINVAL, "null argument");
-    int rc = bind_device(h);
+    BIND_DEVICE(h);
+    int rc = check_sticky(h);
+    if (rc) return rc;
+    rc = order_after_user_stream(h);
     if (rc) return rc;
     const size_t B = h->cfg.n_actors;
     cudaStream_t s = h->own_stream;
@@ -709,6 +761,8 @@ int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host, 
     if (prof) t3 = clk::now();
     std::memcpy(r_int_host, h->r_mapped, B * sizeof(float));
     if (r_epi_host) std::memcpy(r_epi_host, h->r_mapped + B, B * sizeof(float));
+    rc = check_sticky(h);          // the step that just ran may be the one that timed out: its rewards are NaN
+    if (rc) return rc;
     if (prof) {
         const auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
         h->prof_us[0] += us(t0, t1); h->prof_us[1] += us(t1, t2); h->prof_us[2] += us(t2, t3); h->prof_us[3] += us(t3, clk::now());
@@ -719,12 +773,13 @@ int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host, 
 
 int ngu_epi_reset_host(ngu_epi* h, const uint8_t* done_host) {
     if (!h || !done_host) return fail(h, NGU_EINVAL, "null argument");
-    int rc = bind_device(h);
-    if (rc) return rc;
+    BIND_DEVICE(h);
     const int B = h->cfg.n_actors;
     bool any = false;
     for (int b = 0; b < B; ++b) any |= done_host[b] != 0;
     if (!any) return NGU_OK;   // nothing to zero: skip the launch (the common step)
+    int rc = order_after_user_stream(h);
+    if (rc) return rc;
     uint8_t* pd = reinterpret_cast<uint8_t*>(h->pinned + static_cast<size_t>(B) * 33);
     std::memcpy(pd, done_host, B);
     CU_TRY(h, cudaMemcpyAsync(h->done_stage_dev, pd, B, cudaMemcpyHostToDevice, h->own_stream));
@@ -736,8 +791,7 @@ int ngu_epi_reset_host(ngu_epi* h, const uint8_t* done_host) {
 
 int ngu_epi_topk_host(ngu_epi* h, float* d2_host, int32_t* idx_host) {
     if (!h || !d2_host || !idx_host) return fail(h, NGU_EINVAL, "null argument");
-    int rc = bind_device(h);
-    if (rc) return rc;
+    BIND_DEVICE(h);
     CU_TRY(h, cudaDeviceSynchronize());
     const size_t n = static_cast<size_t>(h->cfg.n_actors) * h->cfg.k;
     CU_TRY(h, cudaMemcpy(d2_host, h->topk_d2, n * sizeof(float), cudaMemcpyDeviceToHost));
@@ -745,17 +799,23 @@ int ngu_epi_topk_host(ngu_epi* h, float* d2_host, int32_t* idx_host) {
     return NGU_OK;
 }
 
-int ngu_epi_get_state(ngu_epi* h, ngu_epi_state* out) {
-    if (!h || !out) return fail(h, NGU_EINVAL, "null argument");
-    int rc = bind_device(h);
-    if (rc) return rc;
-    DevState d;
+// Absorb an outstanding reward stash, then read the device state back (synchronous).
+static int read_state(ngu_epi* h, DevState* d) {
     CU_TRY(h, cudaDeviceSynchronize());
-    // bring the log-only trackers up to date (p2p mode: into pending_log; see ngu_epi_log_flush)
+    h->user_stream_dirty = false;
     log_absorb_kernel<<<1, kLogThreads>>>(h->state, h->log_stash, h->cfg.n_actors, h->p2p_connected ? 1 : 0);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaDeviceSynchronize());
-    CU_TRY(h, cudaMemcpy(&d, h->state, sizeof d, cudaMemcpyDeviceToHost));
+    CU_TRY(h, cudaMemcpy(d, h->state, sizeof *d, cudaMemcpyDeviceToHost));
+    return NGU_OK;
+}
+
+int ngu_epi_get_state(ngu_epi* h, ngu_epi_state* out) {
+    if (!h || !out) return fail(h, NGU_EINVAL, "null argument");
+    BIND_DEVICE(h);
+    DevState d;
+    const int rc = read_state(h, &d);   // brings the log-only trackers up to date first (p2p mode: into pending_log)
+    if (rc) return rc;
     std::memcpy(out->ed_mean, d.ed_mean, sizeof d.ed_mean);
     std::memcpy(out->ed_var, d.ed_var, sizeof d.ed_var);
     out->ed_count = d.ed_count;
@@ -769,10 +829,13 @@ int ngu_epi_get_state(ngu_epi* h, ngu_epi_state* out) {
 int ngu_epi_set_state(ngu_epi* h, const ngu_epi_state* in) {
     if (!h || !in) return fail(h, NGU_EINVAL, "null argument");
     if (in->cursor < 0 || in->cursor >= h->cfg.capacity) return fail(h, NGU_EINVAL, "cursor out of range");
-    int rc = bind_device(h);
-    if (rc) return rc;
+    BIND_DEVICE(h);
+    // Only the PUBLIC fields are replaced.  The library's own bookkeeping survives: the log-only sums still waiting
+    // for an exchange round (pending_log), the exchange / flush sequence numbers (tags must stay in step with
+    // the peers) and the sticky timeout counter (the only evidence of a failed merge or exchange).
     DevState d;
-    std::memset(&d, 0, sizeof d);
+    int rc = read_state(h, &d);
+    if (rc) return rc;
     std::memcpy(d.ed_mean, in->ed_mean, sizeof d.ed_mean);
     std::memcpy(d.ed_var, in->ed_var, sizeof d.ed_var);
     d.ed_count = in->ed_count;
@@ -780,14 +843,23 @@ int ngu_epi_set_state(ngu_epi* h, const ngu_epi_state* in) {
     d.intr_mean = in->intr_mean; d.intr_var = in->intr_var; d.intr_count = in->intr_count;
     d.cursor = in->cursor; d.steps = in->steps;
     d.ll_mean = in->ll_mean; d.ll_var = in->ll_var; d.ll_count = in->ll_count;
-    CU_TRY(h, cudaDeviceSynchronize());
     CU_TRY(h, cudaMemcpy(h->state, &d, sizeof d, cudaMemcpyHostToDevice));
     return NGU_OK;
 }
 
+int ngu_epi_set_cursor(ngu_epi* h, int64_t cursor) {
+    if (!h) return fail(h, NGU_EINVAL, "null argument");
+    if (cursor < 0 || cursor >= h->cfg.capacity) return fail(h, NGU_EINVAL, "cursor out of range");
+    BIND_DEVICE(h);
+    CU_TRY(h, cudaDeviceSynchronize());
+    h->user_stream_dirty = false;
+    const long long c = cursor;
+    CU_TRY(h, cudaMemcpy(&h->state->cursor, &c, sizeof c, cudaMemcpyHostToDevice));
+    return NGU_OK;
+}
+
 static int transpose_copy(ngu_epi* h, const float* host_in, float* host_out) {
-    int rc = bind_device(h);
-    if (rc) return rc;
+    BIND_DEVICE(h);
     const int B = h->cfg.n_actors, N = h->cfg.capacity;
     const size_t bytes = static_cast<size_t>(B) * N * 32 * sizeof(float);
     float* tmp = nullptr;
@@ -823,8 +895,7 @@ int ngu_epi_dump_memory_host(ngu_epi* h, float* slot_major_host) {
 int ngu_epi_p2p_export(ngu_epi* h, void* ipc_handle_out, int32_t world) {
     if (!h || !ipc_handle_out) return fail(h, NGU_EINVAL, "null argument");
     if (world < 2 || world > kMaxWorld) return fail(h, NGU_EINVAL, fmt("world must be 2..%d", kMaxWorld));
-    int rc = bind_device(h);
-    if (rc) return rc;
+    BIND_DEVICE(h);
     if (!h->inbox) {
         const size_t bytes = static_cast<size_t>(2) * world * kSlotWords * sizeof(unsigned long long);
         CU_TRY(h, cudaMalloc(&h->inbox, bytes));
@@ -842,8 +913,7 @@ int ngu_epi_p2p_connect(ngu_epi* h, int32_t rank, int32_t world, const void* ipc
     if (!h || !ipc_handles) return fail(h, NGU_EINVAL, "null argument");
     if (!h->inbox) return fail(h, NGU_ESTATE, "call ngu_epi_p2p_export first");
     if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world) return fail(h, NGU_EINVAL, "bad rank/world");
-    int rc = bind_device(h);
-    if (rc) return rc;
+    BIND_DEVICE(h);
     h->p2p = P2PView{};
     h->p2p.inbox = h->inbox; h->p2p.rank = rank; h->p2p.world = world;
     for (int g = 0; g < world; ++g) {
@@ -860,8 +930,7 @@ int ngu_epi_p2p_connect(ngu_epi* h, int32_t rank, int32_t world, const void* ipc
 
 int ngu_epi_log_flush(ngu_epi* h, void* stream) {
     if (!h) return fail(h, NGU_EINVAL, "null argument");
-    int rc = bind_device(h);
-    if (rc) return rc;
+    BIND_DEVICE(h);
     if (!h->p2p_connected) {                  // only the reward stash of the last fused step is outstanding
         log_absorb_kernel<<<1, kLogThreads, 0, static_cast<cudaStream_t>(stream)>>>(h->state, h->log_stash, h->cfg.n_actors, 0);
     } else {
@@ -884,8 +953,7 @@ int ngu_epi_debug_timeline(ngu_epi* h, uint64_t* out_host, int32_t max_warps) {
         return n;
     }
     if (!h->timeline) return fail(h, NGU_ESTATE, "create the handle with NGU_EPI_DEBUG_TIMELINE=1");
-    int rc = bind_device(h);
-    if (rc) return rc;
+    BIND_DEVICE(h);
     int warps = h->grid * h->var.warps;
     if (warps > h->sched.n_chunks) warps = h->sched.n_chunks;
     const int n = warps < max_warps ? warps : max_warps;
@@ -927,6 +995,15 @@ int ngu_epi_debug_chunk(const ngu_epi* h, int32_t idx, int32_t out[2]) {
     return NGU_OK;
 }
 
+int ngu_epi_debug_inject_timeout(ngu_epi* h) {
+    if (!h) return NGU_EINVAL;
+    BIND_DEVICE(h);
+    CU_TRY(h, cudaDeviceSynchronize());
+    const long long one = 1;
+    CU_TRY(h, cudaMemcpy(&h->state->exchange_timeouts, &one, sizeof one, cudaMemcpyHostToDevice));
+    return NGU_OK;
+}
+
 int64_t ngu_epi_launch_count(const ngu_epi* h) { return h ? h->launches : 0; }
 
 static void drop_timing(ngu_epi* h) {
@@ -937,8 +1014,7 @@ static void drop_timing(ngu_epi* h) {
 
 int ngu_epi_scan_timing_begin(ngu_epi* h, int32_t max_calls) {
     if (!h || max_calls < 1) return fail(h, NGU_EINVAL, "bad argument");
-    int rc = bind_device(h);
-    if (rc) return rc;
+    BIND_DEVICE(h);
     drop_timing(h);
     for (int i = 0; i < max_calls; ++i) {
         cudaEvent_t a, b;
@@ -951,8 +1027,7 @@ int ngu_epi_scan_timing_begin(ngu_epi* h, int32_t max_calls) {
 
 int ngu_epi_scan_timing_end(ngu_epi* h, double* total_ms, int32_t* calls) {
     if (!h || !total_ms || !calls) return fail(h, NGU_EINVAL, "null argument");
-    int rc = bind_device(h);
-    if (rc) return rc;
+    BIND_DEVICE(h);
     CU_TRY(h, cudaDeviceSynchronize());
     double tot = 0.0;
     for (size_t i = 0; i < h->t_used; ++i) {

@@ -62,7 +62,10 @@ class Embedding(nn.Module):
         for obs, nxt, act in zip(timestep_obs, timestep_next_obs, timestep_act):
             logits = self.h(torch.cat((self(obs), self(nxt)), dim=1))
             loss = self.criterion(logits, act)
-            self.optimizer.zero_grad()
+            if self.grad_hook is not None:
+                self.grad_hook.zero_grad()          # keeps .grad a view of the communication bucket
+            else:
+                self.optimizer.zero_grad()
             loss.backward()
             if self.grad_hook is not None:          # between backward and clip
                 self.grad_hook(params)

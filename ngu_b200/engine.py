@@ -80,6 +80,8 @@ class EpisodicEngine:
         self._step_host_fn = self._lib.ngu_epi_step_host
         self._out = np.empty((2, self.n_actors), np.float32)      # step_host result staging (address cached)
         self._out_ptr = self._out.ctypes.data
+        self._version = 0            # bumped by every call that can change the running statistics (state cache key)
+        self._state_cache = (-1, None)
 
     # ---- lifetime -----------------------------------------------------------
     def close(self):
@@ -111,10 +113,12 @@ class EpisodicEngine:
 
     # ---- device-pointer path (no host sync) -------------------------------------
     def scan(self, q: torch.Tensor):
+        self._version += 1
         self._q_keep = self._q(q)
         check(self._lib.ngu_epi_scan(self._h, _ptr(self._q_keep), self._stream()), self._h)
 
     def finish(self, sums_global=None, alpha=None, want_log_sums=False):
+        self._version += 1
         if alpha is not None:
             alpha = alpha.to(device=self.device, dtype=torch.float32).contiguous()
         self._alpha_keep = alpha
@@ -123,9 +127,11 @@ class EpisodicEngine:
         return self._r_int, self._r_epi
 
     def log_update(self, log_sums_global: torch.Tensor):
+        self._version += 1
         check(self._lib.ngu_epi_log_update(self._h, _ptr(log_sums_global), self._stream()), self._h)
 
     def append(self, q: torch.Tensor):
+        self._version += 1
         self._q_keep = self._q(q)
         check(self._lib.ngu_epi_append(self._h, _ptr(self._q_keep), self._stream()), self._h)
 
@@ -141,6 +147,7 @@ class EpisodicEngine:
 
     def step(self, q: torch.Tensor, alpha: torch.Tensor | None = None):
         """scan -> finish -> append on the current stream; returns device tensors (r_int, r_epi)."""
+        self._version += 1
         self._q_keep = self._q(q)
         if alpha is not None:
             alpha = alpha.to(device=self.device, dtype=torch.float32).contiguous()
@@ -152,6 +159,7 @@ class EpisodicEngine:
     def step_rnd(self, q: torch.Tensor, pred: torch.Tensor, targ: torch.Tensor):
         """ngu_epi_step_rnd: RND features in, the modulator is computed inside the epilogue kernel.
         Returns device tensors (r_int, r_epi, alpha)."""
+        self._version += 1
         self._q_keep = self._q(q)
         pred = pred.to(device=self.device, dtype=torch.float32).contiguous()
         targ = targ.to(device=self.device, dtype=torch.float32).contiguous()
@@ -185,6 +193,7 @@ class EpisodicEngine:
         the cheaper to pass), host float32 rewards (r_int, r_epi) out as fresh numpy arrays, synchronous."""
         q_ptr, _q = self._host_ptr(q, (self.n_actors, _cabi.DIM), "controllable state")
         a_ptr, _a = (None, None) if alpha is None else self._host_ptr(alpha, (self.n_actors,), "alpha")
+        self._version += 1
         rc = self._step_host_fn(self._h, q_ptr, a_ptr, self._out_ptr, self._out_ptr + 4 * self.n_actors)
         if rc:
             check(rc, self._h)
@@ -205,9 +214,15 @@ class EpisodicEngine:
         check(self._lib.ngu_epi_topk_host(self._h, d2.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p)), self._h)
         return d2, idx
 
-    def get_state(self) -> dict:
+    def get_state(self, allow_failed=False) -> dict:
+        """Running statistics + cursor (synchronous).  Raises if the sticky timeout counter is set
+        (include/ngu_epi.h, "sticky error") unless ``allow_failed``."""
         s = NguEpiState()
         check(self._lib.ngu_epi_get_state(self._h, C.byref(s)), self._h)
+        if s.exchange_timeouts != 0 and not allow_failed:
+            raise _cabi.NguEpiError(
+                f"{s.exchange_timeouts} k-NN merge / p2p exchange round(s) timed out: rewards since then are NaN and "
+                "the replicated statistics may have diverged between ranks; recreate the engine")
         k = self.k
         return dict(ed_mean=np.array(s.ed_mean[:k]), ed_var=np.array(s.ed_var[:k]), ed_count=s.ed_count,
                     epi_mean=s.epi_mean, epi_var=s.epi_var, epi_count=s.epi_count,
@@ -215,7 +230,22 @@ class EpisodicEngine:
                     cursor=int(s.cursor), steps=int(s.steps), exchange_timeouts=int(s.exchange_timeouts),
                     ll_mean=s.ll_mean, ll_var=s.ll_var, ll_count=s.ll_count)
 
+    def cached_state(self) -> dict:
+        """get_state(), fetched once per change of the statistics: a logging step reads six tracker fields
+        (each read used to cost two device synchronisations and a kernel launch)."""
+        if self._state_cache[0] != self._version:
+            self._state_cache = (self._version, self.get_state())
+        return self._state_cache[1]
+
+    def set_cursor(self, cursor: int):
+        """Move only the ring cursor (EpisodicNovelty.memory_idx, episodic_novelty.py:34)."""
+        self._version += 1
+        check(self._lib.ngu_epi_set_cursor(self._h, int(cursor)), self._h)
+
     def set_state(self, st: dict):
+        """Replace the given PUBLIC fields (read-modify-write; the library's own bookkeeping - pending log-only
+        sums, exchange sequence numbers, the sticky timeout counter - is never touched)."""
+        self._version += 1
         s = NguEpiState()
         check(self._lib.ngu_epi_get_state(self._h, C.byref(s)), self._h)
         for j in range(self.k):
@@ -253,6 +283,7 @@ class EpisodicEngine:
 
     def log_flush(self):
         """Collective (p2p mode): bring the one-step-late log-only trackers up to date."""
+        self._version += 1
         check(self._lib.ngu_epi_log_flush(self._h, self._stream()), self._h)
 
     @property

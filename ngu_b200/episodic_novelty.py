@@ -64,7 +64,10 @@ class EpisodicNovelty:
         if self._engine is None and not torch.cuda.is_available():
             self._pending_memory = value
             return
-        self._ensure_engine().episodic_memory.copy_(value.to(self._engine.device))
+        eng = self._ensure_engine()
+        eng.episodic_memory.copy_(value.to(eng.device))
+        # a torch copy is invisible to the library's stream bookkeeping: finish it before any *_host call can run
+        torch.cuda.current_stream(eng.device).synchronize()
 
     @property
     def memory_idx(self) -> int:
@@ -73,7 +76,7 @@ class EpisodicNovelty:
     @memory_idx.setter
     def memory_idx(self, value: int):
         self._memory_idx = int(value) % self.capacity
-        self._ensure_engine().set_state({"cursor": self._memory_idx})
+        self._ensure_engine().set_cursor(self._memory_idx)
 
     # ---- hot path -------------------------------------------------------------------
     def _embed(self, obs) -> torch.Tensor:
@@ -132,6 +135,7 @@ class EpisodicNovelty:
     def load_state_dict(self, sd):
         eng = self._ensure_engine()
         eng.episodic_memory.copy_(sd["memory"].to(eng.device))
-        eng.set_state(sd["engine"])
+        torch.cuda.current_stream(eng.device).synchronize()
+        eng.set_state({k: v for k, v in sd["engine"].items() if k != "exchange_timeouts"})
         self._memory_idx = sd["engine"]["cursor"]
         self.embedding.load_state_dict(sd["embedding"])

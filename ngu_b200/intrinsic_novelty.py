@@ -47,10 +47,12 @@ class IntrinsicNovelty:
         exactly as tests/golden/make_golden.py does to the reference), that modulator is used instead."""
         eng = self.epi_novel._ensure_engine()
         if "compute_lifelong_curiosity" in vars(self.ll_novel):
-            alpha = self.ll_novel.compute_lifelong_curiosity(obs)      # alpha_t, CPU (reference semantics)
-            alpha_dev = torch.as_tensor(alpha).to(device=eng.device, dtype=torch.float32)
-            r_int, _ = self.epi_novel._step(obs, alpha_dev)            # fused: r_epi * clip(alpha, 1, L)
-            return r_int.cpu().unsqueeze(-1)
+            alpha = torch.as_tensor(self.ll_novel.compute_lifelong_curiosity(obs))   # alpha_t, CPU (reference semantics)
+            alpha_dev = alpha.to(device=eng.device, dtype=torch.float32)
+            _, r_epi = self.epi_novel._step(obs, alpha_dev)            # device: r_epi * clip(alpha, 1, L) feeds the log-only tracker
+            # the returned product is formed like the reference's (intrinsic_novelty.py:26-31): clip in alpha's own
+            # dtype (float64 under numpy >= 2), float32 reward promoted by the product
+            return (r_epi.cpu() * alpha.clamp(1.0, self.max_rew)).unsqueeze(-1)
         if self.ll_novel._device_ll_rms is None:
             self.ll_novel._device_ll_rms = DeviceRunningMeanStd(self.epi_novel, "ll", False, 1e-4)
         if self._graphed is not None and tuple(obs.shape[1:]) == tuple(self.epi_novel.obs_shape) \

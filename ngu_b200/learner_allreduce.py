@@ -4,37 +4,46 @@ embedding/RND/R2D2 gradient allreduce runs over NCCL on NVLink").
 The reference has NO gradient averaging anywhere: this is new, data-parallel
 functionality attached at the three seams where gradients exist and clipping has not happened yet:
 
-    ngu/models/intrinsic_novelty/episodic_novelty/embedding.py:60-61      (182,866 params, 0.73 MB)
-    ngu/models/intrinsic_novelty/lifelong_novelty/lifelong_novelty.py:64-65 (473,376 params, 1.89 MB)
-    ngu/models/r2d2/r2d2_learner.py:53-54                                  (8,188,595 params, 32.75 MB)
+    ngu/models/intrinsic_novelty/episodic_novelty/embedding.py:60-61        (182,866 params,  0.73 MB)
+    ngu/models/intrinsic_novelty/lifelong_novelty/lifelong_novelty.py:64-65 (473,376 params,  1.89 MB)
+    ngu/models/r2d2/r2d2_learner.py:53-54                                   (8,188,595 params, 32.75 MB)
 
-``GradAllReducer`` flattens the gradients into a few contiguous buckets and averages them with
-``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in the CPU tests).  With
-``overlap=True`` the buckets are reduced on a side stream as soon as autograd has produced all of
-their gradients (post-accumulate-grad hooks, last layers first), so the transfer of the 32 MB R2D2
-bucket hides behind the rest of backward; ``finish()`` — the call placed at the seam — only waits.
+``GradAllReducer`` owns a few flat, contiguous buckets and makes every parameter's ``.grad`` a VIEW
+of its bucket, so autograd accumulates straight into the communication buffer: a reduction is one
+``ncclAllReduce(avg)`` per bucket, with no copy in, no copy out and no divide kernel (round 1 copied
+both ways and divided: 281 GB/s bus bandwidth on the 32 MB bucket where the fabric gives > 700).
+With ``overlap=True`` a bucket is reduced on a side stream as soon as autograd has produced all of
+its gradients (post-accumulate-grad hooks, last layers first), so the transfer of the R2D2 bucket
+hides behind the rest of backward; the call at the seam then only waits.
 
-Usage at a seam (what ``Embedding.step`` / ``LifelongNovelty.step`` in this package do through their
-``grad_hook`` attribute, and what a maintainer adds to ``R2D2Learner.step``):
+At a seam (what ``Embedding.step`` / ``LifelongNovelty.step`` of this package do through their
+``grad_hook`` attribute, and what ``attach_r2d2_allreduce`` installs on an ``R2D2Learner``):
 
-    reducer = GradAllReducer(params)           # once
+    reducer = GradAllReducer(params)            # once
+    reducer.zero_grad()                          # instead of optimizer.zero_grad(): keeps the views
     loss.backward()
-    reducer(params)                             # <- new line: average over ranks
+    reducer(params)                              # <- new line: average over ranks
     nn.utils.clip_grad_norm_(params, 40)
     optimizer.step()
+
+``optimizer.zero_grad()`` (which drops ``.grad`` to None by default) still works: the reducer then
+copies the fresh gradient tensors into the bucket once and re-installs the views.
 """
 from __future__ import annotations
+
+import types
 
 import torch
 import torch.distributed as dist
 
 
 class GradAllReducer:
-    def __init__(self, params, group=None, bucket_bytes=32 << 20, overlap=False):
+    def __init__(self, params, group=None, bucket_bytes=64 << 20, overlap=False):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.overlap = overlap and self.world > 1
+        self._avg_native = (dist.is_initialized() and dist.get_backend(group) == "nccl")   # gloo has no AVG
         # buckets in reverse order: autograd finishes the last layers first
         self.buckets = []          # list of (flat tensor, [params], [views])
         cur, cur_bytes = [], 0
@@ -51,6 +60,7 @@ class GradAllReducer:
         self._ready = {}
         self._hooks = []
         self._stream = None
+        self.copies_in = 0          # gradients that had to be copied into their bucket (0 in the steady state)
         if self.overlap:
             dev = self.params[0].device
             self._stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
@@ -62,13 +72,42 @@ class GradAllReducer:
         flat = torch.zeros(sum(p.numel() for p in ps), dtype=ps[0].dtype, device=ps[0].device)
         views, off = [], 0
         for p in ps:
-            views.append(flat[off:off + p.numel()].view_as(p))
+            v = flat[off:off + p.numel()].view_as(p)
+            views.append(v)
             off += p.numel()
+            if p.grad is not None:
+                v.copy_(p.grad)
+            p.grad = v                       # autograd accumulates in place from now on
         self.buckets.append((flat, ps, views))
 
     @property
     def nbytes(self):
         return sum(f.numel() * f.element_size() for f, _, _ in self.buckets)
+
+    def zero_grad(self):
+        """Zero the buckets and keep every ``.grad`` a view of its bucket (use instead of optimizer.zero_grad())."""
+        for flat, ps, views in self.buckets:
+            flat.zero_()
+            for p, v in zip(ps, views):
+                if p.grad is not v:
+                    p.grad = v
+
+    def _adopt(self, bi):
+        """Gradients that are not views of the bucket (the caller dropped them with set_to_none): copy them in once
+        and re-install the views."""
+        flat, ps, views = self.buckets[bi]
+        src, dst = [], []
+        for p, v in zip(ps, views):
+            if p.grad is None:
+                v.zero_()
+                p.grad = v
+            elif p.grad.data_ptr() != v.data_ptr():
+                src.append(p.grad)
+                dst.append(v)
+                p.grad = v
+        if src:
+            torch._foreach_copy_(dst, src)
+            self.copies_in += len(src)
 
     # ---- overlapped path: launch a bucket as soon as all of its grads exist -------------------------
     def _make_hook(self, bi):
@@ -79,16 +118,20 @@ class GradAllReducer:
                 self._launch(bi)
         return hook
 
+    def _reduce(self, flat):
+        if self._avg_native:
+            return dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
     def _launch(self, bi):
-        flat, ps, views = self.buckets[bi]
+        flat = self.buckets[bi][0]
+        self._adopt(bi)
         if self._stream is not None:
             self._stream.wait_stream(torch.cuda.current_stream(flat.device))
             with torch.cuda.stream(self._stream):
-                torch._foreach_copy_(views, [p.grad for p in ps])
-                work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                work = self._reduce(flat)
         else:
-            torch._foreach_copy_(views, [p.grad for p in ps])
-            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            work = self._reduce(flat)
         self._pending.append((bi, work))
 
     # ---- the call at the seam -------------------------------------------------------------------------
@@ -96,22 +139,17 @@ class GradAllReducer:
         """Average the gradients over all ranks (in place).  No-op for a single process."""
         if self.world == 1:
             return
-        if self.overlap:
-            launched = {bi for bi, _ in self._pending}
-            for bi in range(len(self.buckets)):      # buckets whose hooks did not all fire (unused params)
-                if bi not in launched and all(p.grad is not None for p in self.buckets[bi][1]):
-                    self._launch(bi)
-        else:
-            for bi, (_, ps, _) in enumerate(self.buckets):
-                if all(p.grad is not None for p in ps):
-                    self._launch(bi)
+        launched = {bi for bi, _ in self._pending}
+        for bi in range(len(self.buckets)):          # not overlapped, or buckets whose hooks did not all fire
+            if bi not in launched:
+                self._launch(bi)
         for bi, work in self._pending:
             work.wait()
-            flat, ps, views = self.buckets[bi]
+            flat = self.buckets[bi][0]
             if self._stream is not None:
                 torch.cuda.current_stream(flat.device).wait_stream(self._stream)
-            flat.div_(self.world)
-            torch._foreach_copy_([p.grad for p in ps], views)
+            if not self._avg_native:
+                flat.div_(self.world)
         self._pending.clear()
         self._ready.clear()
 
@@ -130,3 +168,39 @@ def attach_learner_allreduce(intrinsic_novelty, group=None, overlap=False):
     emb.grad_hook = GradAllReducer(list(emb.parameters()), group, overlap=overlap)
     rnd.grad_hook = GradAllReducer(list(rnd.predictor.parameters()), group, overlap=overlap)
     return emb.grad_hook, rnd.grad_hook
+
+
+def attach_r2d2_allreduce(learner, group=None, overlap=True):
+    """The third seam: ``R2D2Learner.step`` (ngu/models/r2d2/r2d2_learner.py:44-58).
+
+    ``learner`` is the reference's ``R2D2Learner`` (or anything with its attributes: ``policy``, ``optimizer``,
+    ``model_hypr``, ``update_count``, ``r2d2_loss_rms``, ``logger``).  Its ``step`` is replaced by the same
+    statements with the gradient average inserted between ``loss.backward()`` (:53) and
+    ``clip_grad_norm_`` (:54) - the patch a maintainer would make in place:
+
+        -        self.optimizer.zero_grad()
+        +        self.grad_reducer.zero_grad()
+                 loss.backward()
+        +        self.grad_reducer()                     # average over the data-parallel learners
+                 nn.utils.clip_grad_norm_(self.policy.parameters(), self.model_hypr['adam_clip_norm'])
+
+    With ``overlap=True`` the 32.75 MB bucket is split in two so that the head / LSTM gradients travel while the
+    convolution trunk is still in backward.  Returns the reducer.
+    """
+    import torch.nn as nn
+    params = list(learner.policy.parameters())
+    learner.grad_reducer = GradAllReducer(params, group, bucket_bytes=(20 << 20) if overlap else (64 << 20), overlap=overlap)
+
+    def step(self, td_errors, weights):
+        loss = (td_errors.pow(2).mean(dim=0) * weights).mean()                       # r2d2_learner.py:51
+        self.grad_reducer.zero_grad()                                                 # :52 (keeps the bucket views)
+        loss.backward()                                                               # :53
+        self.grad_reducer()                                                           # new: average over ranks
+        nn.utils.clip_grad_norm_(self.policy.parameters(), self.model_hypr['adam_clip_norm'])   # :54
+        self.optimizer.step()                                                         # :55
+        self.update_count += 1                                                        # :56
+        self.r2d2_loss_rms.update(loss.item())                                        # :57
+        self.logger.log_scalar('R2D2Loss', self.r2d2_loss_rms.mean, self.update_count)   # :58
+
+    learner.step = types.MethodType(step, learner)
+    return learner.grad_reducer

@@ -74,7 +74,10 @@ class LifelongNovelty(nn.Module):
         for obs in timestep_obs:
             pred, targ = self(obs)
             loss = self.criterion(targ, pred)
-            self.optimizer.zero_grad()
+            if self.grad_hook is not None:
+                self.grad_hook.zero_grad()          # keeps .grad a view of the communication bucket
+            else:
+                self.optimizer.zero_grad()
             loss.backward()
             if self.grad_hook is not None:
                 self.grad_hook(params)

@@ -46,6 +46,11 @@ class RunningMeanStd:
             self.update_from_moments(float(x), float(x) ** 2, 1)
             return
         n_local = x.shape[0]
+        if not self.use_mpi:
+            # mpi_util.py:51-52: np.mean / np.std in the INPUT dtype (float32 batches give float32 moments),
+            # then np.square(batch_std) (:56)
+            self.update_from_moments(np.mean(x, axis=0), np.square(np.std(x, axis=0)), n_local)
+            return
         x64 = x.astype(np.float64).reshape(n_local, -1)
         if self.use_mpi:
             width = x64.shape[1]
@@ -84,7 +89,7 @@ class DeviceRunningMeanStd:
                 return self._prior
             base = np.zeros(self._k) if field == "mean" else np.ones(self._k)
             return base if self._vector else float(base[0])
-        return eng.get_state()[f"{self._prefix}_{field}"]
+        return eng.cached_state()[f"{self._prefix}_{field}"]
 
     mean = property(lambda self: self._get("mean"))
     var = property(lambda self: self._get("var"))

@@ -26,7 +26,7 @@ def test_exports_every_header_symbol(lib):
     assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.ngu_epi_abi_version() == 3
+    assert lib.ngu_epi_abi_version() == _cabi.ABI_VERSION == int(re.search(r"#define NGU_EPI_ABI_VERSION (\d+)", header).group(1))
 
 
 def test_struct_layout_matches_header():

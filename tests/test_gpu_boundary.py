@@ -1,0 +1,126 @@
+"""GPU tests of the C-ABI boundary behaviour added in round 2: partial state updates that keep the
+library's bookkeeping, the sticky timeout error, stream ordering of the *_host calls behind work the
+caller enqueued on its own stream, and the current-device guard."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-30)
+
+
+def test_set_state_and_set_cursor_keep_bookkeeping(cuda_device):
+    """get -> modify -> set must lose nothing: the reward stash of the last fused step is folded into the
+    log-only trackers, not dropped; set_cursor moves only the cursor (EpisodicNovelty.memory_idx)."""
+    import torch
+    from ngu_b200.engine import EpisodicEngine
+    from oracle.episodic_oracle import EpisodicOracle
+    B, N = 6, 500
+    rng = np.random.default_rng(5)
+    mem0 = rng.standard_normal((N, B, 32), dtype=np.float32)
+    orc = EpisodicOracle(B, N); orc.memory[...] = mem0
+    eng = EpisodicEngine(B, N, device=0); eng.load_memory(mem0)
+    for t in range(6):
+        q = rng.standard_normal((B, 32), dtype=np.float32)
+        want = orc.step(q, None)
+        r_int, _ = eng.step(torch.from_numpy(q).cuda(), None)      # fused step: rewards are stashed for the trackers
+        if t == 2:
+            eng.set_cursor(100); orc.cursor = 100                   # partial update right behind a fused step
+        if t == 4:
+            st = eng.get_state()
+            eng.set_state({"cursor": 7, "ed_count": st["ed_count"]}); orc.cursor = 7
+        assert _rel(r_int.cpu().numpy().astype(np.float64), want["reward"]).max() <= 1e-5
+    st = eng.get_state()
+    assert st["epi_count"] == pytest.approx(1e-4 + 6 * B)          # every step's batch reached the log-only trackers
+    assert st["intr_count"] == pytest.approx(1e-4 + 6 * B)
+    assert st["cursor"] == orc.cursor
+    assert np.array_equal(eng.dump_memory(), orc.memory)
+    with pytest.raises(Exception):
+        eng.set_cursor(N)
+    eng.close()
+
+
+def test_sticky_timeout_error_is_loud(cuda_device):
+    """A merge / exchange that gave up waiting must not produce plausible numbers with rc = 0: rewards become
+    NaN, the next step call returns NGU_ESTATE, get_state raises, set_state cannot clear the counter."""
+    import torch
+    from ngu_b200._cabi import NguEpiError
+    from ngu_b200.engine import EpisodicEngine
+    B, N = 4, 300
+    eng = EpisodicEngine(B, N, device=0)
+    q = torch.randn(B, 32, device="cuda")
+    r, _ = eng.step(q, None)
+    assert torch.isfinite(r).all()
+    assert eng._lib.ngu_epi_debug_inject_timeout(eng._h) == 0
+    r, r_epi = eng.step(q, None)            # launches (the host cannot know yet), but the kernel poisons its output
+    torch.cuda.synchronize()
+    assert torch.isnan(r).all() and torch.isnan(r_epi).all()
+    with pytest.raises(NguEpiError, match="timed out"):
+        eng.step(q, None)
+    with pytest.raises(NguEpiError, match="timed out"):
+        eng.step_host(np.zeros((B, 32), np.float32))
+    with pytest.raises(NguEpiError, match="timed out"):
+        eng.get_state()
+    st = eng.get_state(allow_failed=True)
+    assert st["exchange_timeouts"] == 1
+    eng.set_state({"cursor": 0})
+    assert eng.get_state(allow_failed=True)["exchange_timeouts"] == 1
+    eng.close()
+
+
+def test_host_calls_are_ordered_after_user_stream_work(cuda_device):
+    """insert_state / device-mask reset on the caller's stream, immediately followed by reset_host / step_host on the
+    library's private stream: the private stream must wait (an appended row could land after the
+    zero-fill, a scan could read a half-zeroed memory)."""
+    import torch
+    from ngu_b200.engine import EpisodicEngine
+    from oracle.episodic_oracle import EpisodicOracle
+    B, N = 48, 20000
+    rng = np.random.default_rng(11)
+    mem0 = rng.standard_normal((N, B, 32), dtype=np.float32)
+    orc = EpisodicOracle(B, N, use_c_scan=True); orc.memory[...] = mem0
+    eng = EpisodicEngine(B, N, device=0); eng.load_memory(mem0)
+    side = torch.cuda.Stream()
+    for t in range(6):
+        q = rng.standard_normal((B, 32), dtype=np.float32)
+        done_dev = rng.random(B) < 0.5
+        done_host = rng.random(B) < 0.3
+        q_ins = rng.standard_normal((B, 32), dtype=np.float32)
+        with torch.cuda.stream(side):
+            # a long-running filler first, so that the work below is still queued when the *_host call arrives
+            filler = torch.empty(1 << 28, dtype=torch.uint8, device="cuda"); filler.zero_(); filler.zero_()
+            eng.reset(torch.from_numpy(done_dev).cuda())
+            eng.append(torch.from_numpy(q_ins).cuda())
+        orc.reset(done_dev); orc.append(q_ins)
+        eng.reset_host(done_host); orc.reset(done_host)
+        want = orc.step(q, None)
+        r_int, _ = eng.step_host(q)
+        d2, idx = eng.topk()
+        assert np.array_equal(idx.T, want["idx"]), f"step {t}"
+        assert _rel(r_int.astype(np.float64), want["reward"]).max() <= 1e-5
+        del filler
+    assert np.array_equal(eng.dump_memory(), orc.memory)
+    eng.close()
+
+
+def test_calls_restore_the_current_device(cuda_device):
+    """Every entry point runs on the handle's GPU and puts the caller's current device back."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from ngu_b200.engine import EpisodicEngine
+    torch.cuda.set_device(0)
+    eng = EpisodicEngine(4, 300, device=1)
+    assert torch.cuda.current_device() == 0
+    r, _ = eng.step_host(np.random.default_rng(0).standard_normal((4, 32), dtype=np.float32))
+    dev = C.c_int(-1)
+    C.CDLL("libcudart.so.12").cudaGetDevice(C.byref(dev))
+    assert dev.value == 0 and np.isfinite(r).all()
+    eng.get_state(); eng.topk()
+    C.CDLL("libcudart.so.12").cudaGetDevice(C.byref(dev))
+    assert dev.value == 0
+    eng.close()

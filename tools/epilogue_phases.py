@@ -6,7 +6,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from ngu_b200.engine import EpisodicEngine
 names = ["wait->loaded", "loaded->ranksums", "ranksums->(exchange)", "finish:rms", "finish:rewards", "log sums", "append"]
-for B, N in [(256, 30000), (64, 5000), (1, 30000)]:
+SHAPES = [tuple(int(v) for v in a.split('x')) for a in sys.argv[1:]] or [(256, 30000), (64, 5000), (1, 30000)]
+for B, N in SHAPES:
     eng = EpisodicEngine(B, N, device=0); eng._memory.normal_()
     q = torch.randn(B, 32, device="cuda"); a = 1 + torch.randn(B, device="cuda")
     acc = np.zeros(7); n = 0; tail = 0.0; entry = 0.0; prewait = 0.0

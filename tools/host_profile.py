@@ -3,7 +3,8 @@ os.environ["NGU_EPI_HOST_PROFILE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from ngu_b200.engine import EpisodicEngine
-for B, N in [(256, 30000), (64, 5000)]:
+SHAPES = [tuple(int(v) for v in a.split('x')) for a in sys.argv[1:]] or [(256, 30000), (64, 5000)]
+for B, N in SHAPES:
     eng = EpisodicEngine(B, N, device=0); eng._memory.normal_()
     rng = np.random.default_rng(0)
     q = rng.standard_normal((B, 32), dtype=np.float32); a = (1 + rng.standard_normal(B)).astype(np.float32)

@@ -8,7 +8,8 @@ import numpy as np, torch
 from ngu_b200.engine import EpisodicEngine
 
 pct = lambda x: [round(float(v), 2) for v in np.percentile(x, [0, 50, 100])]
-for B, N in [(1, 30000), (64, 5000), (8, 30000), (256, 1000)]:
+SHAPES = [tuple(int(v) for v in a.split('x')) for a in sys.argv[1:]] or [(1, 30000), (64, 5000), (8, 30000), (256, 1000)]
+for B, N in SHAPES:
     eng = EpisodicEngine(B, N, device=0); eng._memory.normal_()
     q = torch.randn(B, 32, device="cuda"); a = 1 + torch.randn(B, device="cuda")
     for _ in range(50): eng.step(q, a)
