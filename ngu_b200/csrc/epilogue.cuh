@@ -153,6 +153,8 @@ struct EpilogueParams {
     float* alpha_out;         // [B] or null: the modulator computed by the RND phase
     P2PView p2p;              // used when phases & PH_EXCHANGE
     float* log_stash;         // [2][B] r_epi, r_int of the last fused step (PH_LOGFUSE), see log_absorb
+    const unsigned int* arm_go;       // pre-armed launch (ngu_epi_step_host): device word, arm_seq << 1 | cancelled once the stage
+    unsigned int arm_seq;             // kernel has decided (cancelled = nobody rang the doorbell in time); 0 = not pre-armed
     unsigned int* host_err;   // mapped host word: set to 1 when a merge / exchange timed out (sticky error, never cleared)
     unsigned int* host_flag;  // mapped host word or null: receives host_seq after the kernel's last write
     unsigned int host_seq;
@@ -363,6 +365,9 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
     EPI_STAMP(9);
     asm volatile("griddepcontrol.wait;" ::: "memory");               // scan kernel complete, its writes visible
     EPI_STAMP(0);
+    // A pre-armed step whose doorbell never rang: its scan did nothing, and neither does this launch.  (The
+    // stash absorbed above is the same operation ngu_epi_get_state performs: harmless whenever it happens.)
+    if (p.arm_seq != 0u && __ldcg(p.arm_go) == ((p.arm_seq << 1) | 1u)) return;
 
     // ---- one batch of independent loads: everything the phases below need goes on chip ----
     // dist goes global -> shared as 16-byte cp.async (L2 only): every chunk is in flight at once instead of
@@ -742,6 +747,75 @@ __global__ void __launch_bounds__(256) stage_inputs_kernel(float4* __restrict__ 
         asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src_host + i) : "memory");
         dst[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Pre-armed host step (ngu_epi_step_host called back to back).  While step t runs, the host already enqueues the
+// three launches of step t+1: this kernel, the scan and the epilogue, chained with programmatic dependent launch.
+// This one-CTA kernel waits for the host's DOORBELL - a word in mapped host memory the host stores to after it
+// has put the step's inputs into the pinned buffer - and then pulls those inputs over PCIe, exactly like
+// stage_inputs_kernel.  What leaves the critical path of a call: three kernel launches (~9 us of enqueue) and the
+// GPU-side launch latency; the scan's CTAs are already resident behind this kernel, their first tiles prefetched
+// into L2, when the doorbell rings.
+// The wait is BOUNDED (`window_ns`): a caller that does not come back (or synchronises the device) must not find
+// the GPU occupied by a kernel that waits for it.  On timeout, or when the host rings with the cancel bit, the
+// kernel records the cancellation in `go_dev` (the scan and epilogue behind it then exit at once without touching
+// any state) and tells the host through `status_host`; the host then launches the step the ordinary way.
+//   doorbell value : seq << 2 | cancel << 1 | has_alpha
+//   status value   : seq << 1 | cancelled          (acknowledgement: written as soon as the doorbell has been seen)
+//   go value       : seq << 1 | 1                  (device memory, written on cancellation only: read by the scan and the epilogue)
+// ---------------------------------------------------------------------------
+constexpr int kArmThreads = 1024;
+__global__ void __launch_bounds__(kArmThreads) armed_stage_kernel(float4* __restrict__ dst, const float4* src_host, int n_actors,
+                                                                  const unsigned int* doorbell_host, unsigned int seq,
+                                                                  unsigned int* go_dev, unsigned int* status_host,
+                                                                  long long window_ns) {
+    __shared__ unsigned int s_db;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the scan becomes resident behind us and prefetches
+    asm volatile("griddepcontrol.wait;" ::: "memory");                // previous epilogue complete (and, transitively, its scan):
+                                                                      // whoever waits for THIS kernel inherits that order
+    if (threadIdx.x == 0) {
+        unsigned long long t0, t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        unsigned int v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(doorbell_host) : "memory");   // the inputs were written before it
+            if ((v >> 2) == seq) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (static_cast<long long>(t - t0) > window_ns) { v = (seq << 2) | 2u; break; }
+        }
+        *reinterpret_cast<volatile unsigned int*>(status_host) = (seq << 1) | ((v >> 1) & 1u);
+        if (v & 2u) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(go_dev), "r"((seq << 1) | 1u) : "memory");
+        s_db = v;
+    }
+    __syncthreads();
+    const unsigned int v = s_db;
+    if (v & 2u) return;
+    const int n16_q = n_actors * 8;                                   // float4 pieces of the controllable states
+    const int n16_all = (n_actors * 33 + 3) / 4;                      // ... plus the modulators (padded buffers)
+    const int n16 = (v & 1u) ? n16_all : n16_q;
+    // every PCIe read of a batch is in flight before the first result is used: one round trip for up to 4 x 1024 pieces
+    // (256 actors are 2 112 pieces)
+#pragma unroll 1
+    for (int i0 = threadIdx.x; i0 < n16; i0 += 4 * kArmThreads) {
+        float4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kArmThreads;
+            if (i < n16)
+                asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w) : "l"(src_host + i) : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kArmThreads;
+            if (i < n16) dst[i] = x[u];
+        }
+    }
+    if (!(v & 1u)) {                                                  // no modulators: alpha = 1 (clip(1, 1, L) = 1, r * 1 = r)
+        float* a = reinterpret_cast<float*>(dst) + static_cast<size_t>(n_actors) * 32;
+        for (int i = threadIdx.x; i < n_actors; i += kArmThreads) a[i] = 1.0f;
     }
 }
 

@@ -122,8 +122,22 @@ struct ngu_epi {
     unsigned long long* epi_stamps = nullptr;   // NGU_EPI_DEBUG_EPILOGUE=1: phase stamps of the last epilogue launch
     // staging for the *_host entry points
     cudaStream_t own_stream = nullptr;
-    float* q_stage_dev = nullptr;    // [B][32] followed by alpha [B]: one H2D copy per step
-    float* a_stage_dev = nullptr;    // = q_stage_dev + B*32
+    float* q_stage_dev = nullptr;    // 2 x {[B][32] q, [B] alpha}: one H2D transfer per step, buffers alternate with the step
+                                     // parity (a pre-armed step stages its inputs while the previous epilogue may still read its own)
+    size_t q_stage_stride = 0;       // floats between the two buffers
+    // pre-armed host step (armed_stage_kernel, epilogue.cuh)
+    bool arm_enabled = true;         // NGU_EPI_HOST_ARM=0 switches it off
+    long long arm_window_ns = 150000;   // NGU_EPI_ARM_WINDOW_US: how long an armed step waits for the doorbell
+    unsigned int arm_seq_next = 0;   // set while enqueue_armed builds its launches: they carry this sequence number
+    unsigned int armed_seq = 0;      // host_seq value the enqueued, waiting launches belong to (0 = none)
+    unsigned int* doorbell = nullptr;        // = flag_mapped + 16 (own 64-byte line): host -> GPU
+    unsigned int* doorbell_dev = nullptr;
+    unsigned int* arm_status = nullptr;      // = flag_mapped + 32: GPU -> host acknowledgement
+    unsigned int* arm_status_dev = nullptr;
+    unsigned int* arm_cancel_dev = nullptr;  // device word `go`: seq << 1 | cancelled, stored by armed_stage_kernel, polled by the armed scan
+    std::chrono::steady_clock::time_point last_return{};   // when the previous ngu_epi_step_host returned
+    bool have_last_return = false;
+    long arm_hits = 0, arm_misses = 0;       // armed steps that ran / were cancelled (host profile)
     uint8_t* done_stage_dev = nullptr;
     float* pinned = nullptr;         // host, mapped: [B*32 q][B alpha] floats + B done bytes
     float* pinned_dev = nullptr;     // device alias of pinned (stage_inputs_kernel reads it over PCIe)
@@ -175,6 +189,23 @@ int fail(ngu_epi* h, int code, const std::string& msg) {
             return fail(h, NGU_ECUDA, fmt("%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__)); \
     } while (0)
 
+// Pre-armed host step: launches of the NEXT ngu_epi_step_host may be sitting in the private stream, waiting for the
+// doorbell.  Every other entry point cancels them first (they exit without touching any state), so that nothing it
+// enqueues or synchronises on has to sit out the doorbell window.  Returns when the cancellation is acknowledged.
+void disarm(ngu_epi* h) {
+    if (h->armed_seq == 0u) return;
+    const unsigned int seq = h->armed_seq;
+    h->armed_seq = 0u;
+    __atomic_store_n(h->doorbell, (seq << 2) | 2u, __ATOMIC_RELEASE);
+    volatile unsigned int* st = h->arm_status;
+    for (unsigned spins = 1; (*st >> 1) != seq; ++spins) {
+        if ((spins & 0xFFFFu) == 0u && cudaStreamQuery(h->own_stream) != cudaErrorNotReady) break;   // drained or failed
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    h->arm_misses += 1;
+}
 // Every entry point runs on the handle's GPU and leaves the caller's current device as it found it
 // (a handle on cuda:1 must not silently switch a thread whose torch current device is cuda:0).
 struct DeviceGuard {
@@ -188,7 +219,8 @@ struct DeviceGuard {
     DeviceGuard(const DeviceGuard&) = delete;
     DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
-#define BIND_DEVICE(h) DeviceGuard dev_guard_(h); if (dev_guard_.rc) return dev_guard_.rc
+#define BIND_DEVICE_KEEP_ARMED(h) DeviceGuard dev_guard_(h); if (dev_guard_.rc) return dev_guard_.rc
+#define BIND_DEVICE(h) BIND_DEVICE_KEEP_ARMED(h); disarm(h)
 
 // Sticky error: once a merge or an exchange round has timed out (DevState::exchange_timeouts != 0, mirrored by
 // the epilogue into a mapped host word) every later result is wrong - the step entry points refuse to go on.
@@ -448,8 +480,11 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
         CREATE_TRY(cudaMemcpy(h->plan_dev, plan.data(), plan.size() * sizeof(int2), cudaMemcpyHostToDevice));
     }
     CREATE_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    CREATE_TRY(cudaMalloc(&h->q_stage_dev, static_cast<size_t>(B) * 33 * sizeof(float) + 16));
-    h->a_stage_dev = h->q_stage_dev + static_cast<size_t>(B) * 32;
+    h->q_stage_stride = (static_cast<size_t>(B) * 33 + 4 + 31) / 32 * 32;       // floats; keeps both buffers 128-byte aligned
+    CREATE_TRY(cudaMalloc(&h->q_stage_dev, 2 * h->q_stage_stride * sizeof(float)));
+    CREATE_TRY(cudaMemset(h->q_stage_dev, 0, 2 * h->q_stage_stride * sizeof(float)));
+    CREATE_TRY(cudaMalloc(&h->arm_cancel_dev, 64));
+    CREATE_TRY(cudaMemset(h->arm_cancel_dev, 0, 64));
     CREATE_TRY(cudaMalloc(&h->done_stage_dev, static_cast<size_t>(B)));
     CREATE_TRY(cudaHostAlloc(&h->pinned, static_cast<size_t>(B) * 33 * sizeof(float) + B + 16, cudaHostAllocMapped));
     CREATE_TRY(cudaHostGetDevicePointer(&h->pinned_dev, h->pinned, 0));
@@ -459,11 +494,16 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
     if (const char* e = getenv("NGU_EPI_HOST_STAGE")) h->stage_by_kernel = std::strcmp(e, "copy") != 0;
     CREATE_TRY(cudaHostAlloc(&h->r_mapped, static_cast<size_t>(B) * 2 * sizeof(float), cudaHostAllocMapped));
     CREATE_TRY(cudaHostGetDevicePointer(&h->r_mapped_dev, h->r_mapped, 0));
-    CREATE_TRY(cudaHostAlloc(&h->flag_mapped, 64, cudaHostAllocMapped));
+    CREATE_TRY(cudaHostAlloc(&h->flag_mapped, 256, cudaHostAllocMapped));
     CREATE_TRY(cudaHostGetDevicePointer(&h->flag_mapped_dev, h->flag_mapped, 0));
     *h->flag_mapped = 0u;
     h->err_mapped = h->flag_mapped + 8; h->err_mapped_dev = h->flag_mapped_dev + 8;
     *h->err_mapped = 0u;
+    h->doorbell = h->flag_mapped + 16; h->doorbell_dev = h->flag_mapped_dev + 16;
+    h->arm_status = h->flag_mapped + 32; h->arm_status_dev = h->flag_mapped_dev + 32;
+    *h->doorbell = 0u; *h->arm_status = 0u;
+    if (const char* e = getenv("NGU_EPI_HOST_ARM")) h->arm_enabled = atoi(e) != 0;
+    if (const char* e = getenv("NGU_EPI_ARM_WINDOW_US")) h->arm_window_ns = atoll(e) * 1000ll;
     CREATE_TRY(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
 
     if (const char* e = getenv("NGU_EPI_HOST_PATH")) h->host_flag_wait = std::strcmp(e, "sync") != 0;
@@ -491,10 +531,12 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
 void ngu_epi_destroy(ngu_epi* h) {
     if (!h) return;
     if (h->host_profile && h->prof_calls > 0)
-        fprintf(stderr, "[ngu_epi] step_host x%ld: stage-in %.2f us, enqueue %.2f us, wait %.2f us, copy-out %.2f us per call\n",
+        fprintf(stderr, "[ngu_epi] step_host x%ld: stage-in %.2f us, enqueue %.2f us, wait %.2f us, copy-out %.2f us per call; "
+                        "pre-armed steps run %ld, cancelled %ld\n",
                 h->prof_calls, h->prof_us[0] / h->prof_calls, h->prof_us[1] / h->prof_calls, h->prof_us[2] / h->prof_calls,
-                h->prof_us[3] / h->prof_calls);
+                h->prof_us[3] / h->prof_calls, h->arm_hits, h->arm_misses);
     DeviceGuard dev_guard_(h);
+    disarm(h);
     if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
     for (cudaEvent_t e : h->t_beg) cudaEventDestroy(e);
     for (cudaEvent_t e : h->t_end) cudaEventDestroy(e);
@@ -506,7 +548,7 @@ void ngu_epi_destroy(ngu_epi* h) {
     if (h->owns_memory) cudaFree(h->memory);
     cudaFree(h->cand); cudaFree(h->topk_d2); cudaFree(h->topk_idx); cudaFree(h->dist);
     cudaFree(h->rank_sums); cudaFree(h->log_sums); cudaFree(h->log_stash); cudaFree(h->state); cudaFree(h->actor_state); cudaFree(h->sched_ctr); cudaFree(h->leftover); cudaFree(h->plan_dev); cudaFree(h->timeline); cudaFree(h->epi_stamps);
-    cudaFree(h->q_stage_dev); cudaFree(h->done_stage_dev);
+    cudaFree(h->q_stage_dev); cudaFree(h->done_stage_dev); cudaFree(h->arm_cancel_dev);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->r_mapped) cudaFreeHost(h->r_mapped);
     if (h->flag_mapped) cudaFreeHost(h->flag_mapped);
@@ -552,6 +594,7 @@ static int launch_scan(ngu_epi* h, const float* q_dev, cudaStream_t s) {
     sp.timeouts = reinterpret_cast<unsigned long long*>(&h->state->exchange_timeouts);
     sp.topk_d2 = h->topk_d2; sp.topk_idx = h->topk_idx; sp.dist = h->dist;
     sp.timeline = h->timeline;
+    sp.arm_go = h->arm_cancel_dev; sp.arm_seq = h->arm_seq_next;
     sp.debug = h->debug_scan;
     void* args[] = {&h->tmap, &sp};
     const bool timed = h->t_used < h->t_beg.size();
@@ -571,6 +614,7 @@ static int launch_epilogue(ngu_epi* h, int phases, const double* sums_in, const 
     EpilogueParams ep{};
     if (hf) { ep.host_flag = hf->flag; ep.host_seq = hf->seq; }
     ep.host_err = h->err_mapped_dev;
+    ep.arm_go = h->arm_cancel_dev; ep.arm_seq = h->arm_seq_next;
     ep.dbg_stamps = h->epi_stamps;
     if (rnd) { ep.rnd_pred = rnd->pred; ep.rnd_targ = rnd->targ; ep.alpha_out = rnd->alpha_out; }
     ep.dist = h->dist; ep.rank_sums = h->rank_sums; ep.sums_in = sums_in; ep.alpha = alpha;
@@ -706,7 +750,10 @@ static int wait_host_flag(ngu_epi* h, unsigned int seq, cudaStream_t s) {
         if (*f == seq) return NGU_OK;
         if ((spins & 0xFFFu) == 0u) {
             const cudaError_t e = cudaStreamQuery(s);
-            if (e == cudaSuccess) return NGU_OK;          // completed: every write of the step is visible
+            if (e == cudaSuccess) {                       // drained: every write of the step is visible by now
+                if (*f == seq) return NGU_OK;
+                return fail(h, NGU_ECUDA, "the stream drained without the step signalling completion");
+            }
             if (e != cudaErrorNotReady) return fail(h, NGU_ECUDA, fmt("step failed: %s", cudaGetErrorString(e)));
         }
 #if defined(__x86_64__) || defined(__i386__)
@@ -715,42 +762,102 @@ static int wait_host_flag(ngu_epi* h, unsigned int seq, cudaStream_t s) {
     }
 }
 
+// Enqueue the three launches of host step `seq` in pre-armed form: armed_stage_kernel (waits for the doorbell, pulls
+// the inputs), scan, epilogue - the latter two exit at once if the stage kernel reports a cancellation.
+static int enqueue_armed(ngu_epi* h, unsigned int seq) {
+    const size_t B = h->cfg.n_actors;
+    cudaStream_t s = h->own_stream;
+    float* stage = h->q_stage_dev + (seq & 1u) * h->q_stage_stride;
+    {
+        float4* dst = reinterpret_cast<float4*>(stage);
+        const float4* src = reinterpret_cast<const float4*>(h->pinned_dev);
+        int n_actors = static_cast<int>(B);
+        const unsigned int* db = h->doorbell_dev;
+        unsigned int* cancel = h->arm_cancel_dev;
+        unsigned int* status = h->arm_status_dev;
+        long long window = h->arm_window_ns;
+        void* args[] = {&dst, &src, &n_actors, &db, &seq, &cancel, &status, &window};
+        CU_TRY(h, launch_pdl(reinterpret_cast<const void*>(&armed_stage_kernel), dim3(1), dim3(kArmThreads), 0, s, true, args));
+        h->launches += 1;
+    }
+    const HostFlag hf{h->flag_mapped_dev, seq};
+    h->arm_seq_next = seq;                       // picked up by launch_scan / launch_epilogue
+    int rc = step_impl(h, stage, stage + B * 32, h->r_mapped_dev, h->r_mapped_dev + B, s, &hf);
+    h->arm_seq_next = 0u;
+    if (rc) return rc;
+    h->armed_seq = seq;
+    return NGU_OK;
+}
+
 int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host, float* r_int_host,
                       float* r_epi_host) {
     if (!h || !q_host || !r_int_host) return fail(h, NGU_EINVAL, "null argument");
-    BIND_DEVICE(h);
+    BIND_DEVICE_KEEP_ARMED(h);
     int rc = check_sticky(h);
     if (rc) return rc;
-    rc = order_after_user_stream(h);
-    if (rc) return rc;
+    using clk = std::chrono::steady_clock;
+    const clk::time_point t0 = clk::now();
+    if (h->user_stream_dirty) {            // (other entry points have already cancelled an armed step)
+        rc = order_after_user_stream(h);
+        if (rc) return rc;
+    }
     const size_t B = h->cfg.n_actors;
     cudaStream_t s = h->own_stream;
-    using clk = std::chrono::steady_clock;
     const bool prof = h->host_profile;
-    clk::time_point t0, t1, t2, t3;
-    if (prof) t0 = clk::now();
+    clk::time_point t1, t2, t3;
     const unsigned int seq = ++h->host_seq;
-    const HostFlag hf{h->flag_mapped_dev, seq};
-    // one pinned H2D copy carries the step's controllable states and (optionally) the modulators
+    // one pinned buffer carries the step's controllable states and (optionally) the modulators
     std::memcpy(h->pinned, q_host, B * 32 * sizeof(float));
     if (alpha_host) std::memcpy(h->pinned + B * 32, alpha_host, B * sizeof(float));
     if (prof) t1 = clk::now();
-    if (h->stage_by_kernel && h->use_pdl) {
-        // whole 16-byte pieces: both buffers are padded, a few floats past the modulators ride along
-        const int n16 = static_cast<int>((B * (alpha_host ? 33 : 32) + 3) / 4);
-        stage_inputs_kernel<<<(n16 + 255) / 256, 256, 0, s>>>(reinterpret_cast<float4*>(h->q_stage_dev),
-                                                              reinterpret_cast<const float4*>(h->pinned_dev), n16);
-        CU_TRY(h, cudaGetLastError());
-        h->launches += 1;
-    } else {
-        CU_TRY(h, cudaMemcpyAsync(h->q_stage_dev, h->pinned, B * (alpha_host ? 33 : 32) * sizeof(float),
-                                  cudaMemcpyHostToDevice, s));
+
+    bool running = false;
+    if (h->armed_seq == seq) {
+        // The launches of this step are already in the stream, waiting: ring the doorbell.  The stage kernel
+        // acknowledges at once (accepted, or cancelled if its window had just run out).
+        h->armed_seq = 0u;
+        __atomic_store_n(h->doorbell, (seq << 2) | (alpha_host ? 1u : 0u), __ATOMIC_RELEASE);
+        volatile unsigned int* st = h->arm_status;
+        unsigned int v;
+        for (unsigned spins = 1; ((v = *st) >> 1) != seq; ++spins) {
+            if ((spins & 0xFFFFu) == 0u) {
+                const cudaError_t e = cudaStreamQuery(s);
+                if (e != cudaErrorNotReady && e != cudaSuccess) return fail(h, NGU_ECUDA, fmt("step failed: %s", cudaGetErrorString(e)));
+            }
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+        }
+        running = (v & 1u) == 0u;
+        if (running) h->arm_hits += 1; else h->arm_misses += 1;
+    } else if (h->armed_seq != 0u) {
+        disarm(h);                               // (cannot happen: armed steps are always the next sequence number)
     }
-    const float* q_dev = h->q_stage_dev;
-    // the rewards come back zero-copy: the epilogue writes them straight into mapped host memory
-    rc = step_impl(h, q_dev, alpha_host ? q_dev + B * 32 : nullptr, h->r_mapped_dev, h->r_mapped_dev + B, s,
-                   h->host_flag_wait ? &hf : nullptr);
-    if (rc) return rc;
+    if (!running) {
+        float* stage = h->q_stage_dev + (seq & 1u) * h->q_stage_stride;
+        if (h->stage_by_kernel && h->use_pdl) {
+            // whole 16-byte pieces: both buffers are padded, a few floats past the modulators ride along
+            const int n16 = static_cast<int>((B * (alpha_host ? 33 : 32) + 3) / 4);
+            stage_inputs_kernel<<<(n16 + 255) / 256, 256, 0, s>>>(reinterpret_cast<float4*>(stage),
+                                                                  reinterpret_cast<const float4*>(h->pinned_dev), n16);
+            CU_TRY(h, cudaGetLastError());
+            h->launches += 1;
+        } else {
+            CU_TRY(h, cudaMemcpyAsync(stage, h->pinned, B * (alpha_host ? 33 : 32) * sizeof(float), cudaMemcpyHostToDevice, s));
+        }
+        const HostFlag hf{h->flag_mapped_dev, seq};
+        // the rewards come back zero-copy: the epilogue writes them straight into mapped host memory
+        rc = step_impl(h, stage, alpha_host ? stage + B * 32 : nullptr, h->r_mapped_dev, h->r_mapped_dev + B, s,
+                       h->host_flag_wait ? &hf : nullptr);
+        if (rc) return rc;
+    }
+    // While this step runs: enqueue the next one in pre-armed form - if the caller is in a tight loop (it came back
+    // within the doorbell window last time); a sporadic caller never leaves anything waiting on the GPU.
+    if (h->arm_enabled && h->use_pdl && h->host_flag_wait && h->have_last_return &&
+        std::chrono::duration_cast<std::chrono::nanoseconds>(t0 - h->last_return).count() * 2 < h->arm_window_ns) {
+        rc = enqueue_armed(h, seq + 1u);
+        if (rc) return rc;
+    }
     if (prof) t2 = clk::now();
     if (h->host_flag_wait) {
         rc = wait_host_flag(h, seq, s);
@@ -763,9 +870,11 @@ int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host, 
     if (r_epi_host) std::memcpy(r_epi_host, h->r_mapped + B, B * sizeof(float));
     rc = check_sticky(h);          // the step that just ran may be the one that timed out: its rewards are NaN
     if (rc) return rc;
+    h->last_return = clk::now();
+    h->have_last_return = true;
     if (prof) {
         const auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
-        h->prof_us[0] += us(t0, t1); h->prof_us[1] += us(t1, t2); h->prof_us[2] += us(t2, t3); h->prof_us[3] += us(t3, clk::now());
+        h->prof_us[0] += us(t0, t1); h->prof_us[1] += us(t1, t2); h->prof_us[2] += us(t2, t3); h->prof_us[3] += us(t3, h->last_return);
         h->prof_calls += 1;
     }
     return NGU_OK;

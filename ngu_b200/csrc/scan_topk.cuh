@@ -126,6 +126,9 @@ struct ScanParams {
     float* topk_d2;          // [B][k]
     int32_t* topk_idx;       // [B][k]
     float* dist;             // [B][k]
+    const unsigned int* arm_go;       // pre-armed launch (ngu_epi_step_host, see armed_stage_kernel): device word the stage kernel
+    unsigned int arm_seq;             // sets to arm_seq << 1 | cancelled when the step's inputs are in place (or the step is
+                                      // cancelled); arm_seq == 0: an ordinary launch
     unsigned long long* timeline;  // debug (tools/scan_timeline.py): per warp {start, first tile, scan end, flush end, smid} (8 words), or null
     int32_t debug;           // experiments only (NGU_EPI_DEBUG_SCAN): 1 = no top-k offers, 2 = no distance math, 4 = no flush,
                              // 8 = no merge, 16 = no floor seeding, 32 = no L2 prefetch before the grid dependency
@@ -723,6 +726,11 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
     }
     __syncwarp();
     pdl_wait();   // predecessor (previous step's epilogue: append, readers of dist/topk) is complete
+    // A pre-armed step (ngu_epi_step_host, armed_stage_kernel) whose doorbell never rang: leave without touching
+    // anything (the exit releases the epilogue behind us, which does the same).
+    // (Measured and rejected: polling this word for "go" instead of waiting for the stage kernel to exit.  With
+    // 2 368 resident warps polling one line the release store queues behind them: +3 us at 256 x 30k, -1 us at 1 x 30k.)
+    if (p.arm_seq != 0u && __ldcg(p.arm_go) == ((p.arm_seq << 1) | 1u)) return;
     // Only now may this step's epilogue become resident (it waits on us): signalled AFTER the wait, so that an
     // epilogue CTA never runs concurrently with the previous epilogue - its pre-wait section reads state the
     // previous one writes (epilogue.cuh, log_absorb).  Costs nothing: it could not become resident before one of

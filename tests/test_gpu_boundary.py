@@ -124,3 +124,70 @@ def test_calls_restore_the_current_device(cuda_device):
     C.CDLL("libcudart.so.12").cudaGetDevice(C.byref(dev))
     assert dev.value == 0
     eng.close()
+
+
+@pytest.mark.parametrize("B,N", [(5, 700), (64, 5000), (256, 2000)])
+def test_pre_armed_host_steps_vs_oracle(cuda_device, monkeypatch, B, N):
+    """ngu_epi_step_host in a tight loop: from the second call on the next step's launches are enqueued ahead and
+    released by the doorbell (armed_stage_kernel).  Every way such a step can end is exercised against the oracle:
+    doorbell in time (with and without modulators), the window running out while the caller sleeps, cancellation by
+    another entry point (topk / reset_host / get_state / a device-pointer step)."""
+    import time
+    import torch
+    from ngu_b200.engine import EpisodicEngine
+    from oracle.episodic_oracle import EpisodicOracle
+    monkeypatch.setenv("NGU_EPI_HOST_PROFILE", "1")
+    monkeypatch.setenv("NGU_EPI_ARM_WINDOW_US", "300")
+    rng = np.random.default_rng(B * 7 + N)
+    mem0 = rng.standard_normal((N, B, 32), dtype=np.float32)
+    orc = EpisodicOracle(B, N, use_c_scan=True); orc.memory[...] = mem0
+    eng = EpisodicEngine(B, N, device=0); eng.load_memory(mem0)
+    T = 60
+    qs = rng.standard_normal((T, B, 32), dtype=np.float32)
+    al = (1.0 + 2.0 * rng.standard_normal((T, B))).astype(np.float32)
+    got = []
+    t = 0
+    while t < T:
+        kind = (t // 6) % 5
+        if kind in (0, 1):                       # tight loop: armed steps run
+            for _ in range(6):
+                got.append(eng.step_host(qs[t], al[t] if (t % 2 or kind == 0) else None)[0]); t += 1
+        elif kind == 2:                          # the caller goes away for longer than the window
+            for _ in range(6):
+                got.append(eng.step_host(qs[t], al[t])[0]); t += 1
+                if t % 2:
+                    time.sleep(0.002)
+        elif kind == 3:                          # other entry points in between cancel the armed step
+            for i in range(6):
+                got.append(eng.step_host(qs[t], al[t])[0]); t += 1
+                if i % 3 == 0:
+                    eng.topk()
+                elif i % 3 == 1:
+                    eng.get_state()
+                else:
+                    eng.reset_host(np.zeros(B, np.uint8) + (np.arange(B) == (t % B)))
+                    orc_done = (np.arange(B) == (t % B))
+                    got.append(("reset", orc_done))
+        else:                                    # device-pointer steps interleaved with host steps
+            for i in range(6):
+                if i % 2:
+                    r = eng.step(torch.from_numpy(qs[t]).cuda(), torch.from_numpy(al[t]).cuda())[0].cpu().numpy()
+                else:
+                    r = eng.step_host(qs[t], al[t])[0]
+                got.append(r); t += 1
+    # replay on the oracle
+    t = 0
+    worst = 0.0
+    for item in got:
+        if isinstance(item, tuple):
+            orc.reset(item[1]); continue
+        kind = (t // 6) % 5
+        alpha = al[t] if not (kind == 1 and t % 2 == 0) else None
+        want = orc.step(qs[t], alpha)["reward"]
+        worst = max(worst, float(_rel(item.astype(np.float64), want).max()))
+        t += 1
+    assert worst <= 1e-5, worst
+    assert np.array_equal(eng.dump_memory(), orc.memory)
+    st = eng.get_state()
+    assert st["exchange_timeouts"] == 0 and st["steps"] == T
+    eng.close()

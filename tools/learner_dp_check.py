@@ -57,15 +57,24 @@ def unroll_td(policy, obs, act, rew_i, rew_e, beta, T):
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    cuda = torch.cuda.is_available()              # (CPU + gloo: a dry run of the script's logic in the build container)
+    if cuda:
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dev = torch.device("cpu")
+        dist.init_process_group("gloo")
+    sync = torch.cuda.synchronize if cuda else (lambda: None)
     from ngu_b200.learner_allreduce import GradAllReducer, attach_r2d2_allreduce
 
     T, Bg = 8, 8 * world                               # global batch, sliced over the ranks
     g = torch.Generator().manual_seed(5)
     obs = torch.randn(T, Bg, 1, 84, 84, generator=g).to(dev)
-    act = torch.randint(0, 18, (T, Bg), generator=g).to(dev)
+    # one action per time step for the whole batch: the reference's make_one_hot_batch (pytorch_util.py:52-56) sets the
+    # columns of EVERY row from all indices of the batch, so with per-sample actions a slice of the batch would not see
+    # the inputs the full batch sees
+    act = (torch.arange(T) % 18).view(T, 1).expand(T, Bg).contiguous().to(dev)
     rew_i = torch.randn(T, Bg, 1, generator=g).to(dev)
     rew_e = torch.randn(T, Bg, 1, generator=g).to(dev)
     beta = torch.zeros(Bg, 32, device=dev)
@@ -96,11 +105,7 @@ def main():
             # equal slices: mean over the local slice, averaged over ranks == mean over the whole batch
             learner.step(td, w[lo:hi])
         learner.optimizer.step = orig
-        worst = 0.0
-        for a, b in zip(grads["g"], full):
-            # compare after the same clip the step applied (clip_grad_norm_ scales by a global factor <= 1)
-            worst = max(worst, float((a - b).abs().max() / (b.abs().max() + 1e-12)))
-        # the clip factor: recompute on the full gradient
+        # compare after the same clip the step applied (clip_grad_norm_ scales by a global factor <= 1)
         tot = torch.sqrt(sum((f.double() ** 2).sum() for f in full)).item()
         scale = min(1.0, hy["adam_clip_norm"] / (tot + 1e-6))
         worst_scaled = 0.0
@@ -124,7 +129,7 @@ def main():
         red.close()
 
     # ---- timing: does the all-reduce hide behind backward? ----
-    def timed(mode, iters=20):
+    def timed(mode, iters=20 if cuda else 1):
         learner, hy = build_learner()
         params = list(learner.policy.parameters())
         red = GradAllReducer(params, bucket_bytes=(20 << 20) if mode == "overlap" else (64 << 20),
@@ -144,13 +149,13 @@ def main():
                 red.zero_grad()
             else:
                 learner.optimizer.zero_grad(set_to_none=False)
-            torch.cuda.synchronize()
+            sync()
             dist.barrier()
             t0 = time.perf_counter()
             loss.backward()
             if red is not None:
                 red()
-            torch.cuda.synchronize()
+            sync()
             if it >= 3:
                 tot += time.perf_counter() - t0
         if red is not None:
@@ -169,16 +174,19 @@ def main():
         red = GradAllReducer(ps)
         for _ in range(10):
             red()
-        torch.cuda.synchronize()
+        sync()
         dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        iters = 100
-        e0.record()
+        iters = 100 if cuda else 3
+        t0 = time.perf_counter()
+        if cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         for _ in range(iters):
             red()
-        e1.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+        if cuda:
+            e1.record()
+        sync()
+        t = torch.tensor([e0.elapsed_time(e1) / iters if cuda else (time.perf_counter() - t0) * 1e3 / iters], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         bw[name] = {"bytes": n * 4, "ms": round(ms, 4), "algbw_GBs": round(n * 4 / ms / 1e6, 1),
