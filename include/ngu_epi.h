@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define NGU_EPI_ABI_VERSION 4
+#define NGU_EPI_ABI_VERSION 5
 #define NGU_EPI_DIM 32          /* controllable_state_dim, episodic_novelty.py:23 */
 #define NGU_EPI_MAX_K 32        /* k-NN list lives in one warp */
 
@@ -170,6 +170,24 @@ int ngu_epi_reset(ngu_epi* h, const uint8_t* done_dev, void* stream);
  * alpha is float64 under numpy >= 2 (intrinsic_novelty.py:31); the values agree to float32 rounding. */
 int ngu_epi_step(ngu_epi* h, const float* q_dev, const float* alpha_dev,
                  float* r_int_dev, float* r_epi_dev, void* stream);
+
+/* ngu_epi_step for callers that enqueue steps BACK TO BACK with inputs that are already on the device (a sequence of
+ * precomputed controllable states; bench.py's device-resident loop): the step is software-pipelined with the previous
+ * one.  Step s+1 depends on step s only through the one slot per actor that step s appends to
+ * (episodic_novelty.py:80,86-89 - the query at :51-54 reads the memory, the append writes one row), so this call's
+ * scan kernel does not wait for the previous step's epilogue: it streams while that step's k-NN merge tail, its
+ * reward epilogue and (connected ranks) its NVLink exchange are still running, and takes the content of the slot
+ * being appended from the previous call's q_dev.  Results are identical to ngu_epi_step's, bit for bit.
+ * The caller promises, for a call that directly follows another ngu_epi_step / ngu_epi_step_pipelined on the same
+ * stream (any other call on the handle in between, a different stream, or a stream capture makes this call behave
+ * exactly like ngu_epi_step):
+ *   - nothing else was enqueued on `stream` since that previous call;
+ *   - q_dev / alpha_dev of THIS call were complete before the previous call was made (or are written by work that
+ *     was enqueued on `stream` before it) - they may be read as soon as the previous step starts;
+ *   - the previous call's q_dev stays intact until this step has completed;
+ *   - r_int_dev / r_epi_dev are written in step order, as with ngu_epi_step. */
+int ngu_epi_step_pipelined(ngu_epi* h, const float* q_dev, const float* alpha_dev,
+                           float* r_int_dev, float* r_epi_dev, void* stream);
 
 /* ngu_epi_step with the scalar tail of LifelongNovelty.compute_lifelong_curiosity fused in
  * (lifelong_novelty.py:53-57): instead of a ready-made modulator the caller passes the RND

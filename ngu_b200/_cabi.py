@@ -14,7 +14,7 @@ from .build import LIB_PATH
 MAX_K = 32
 DIM = 32
 MODE_REFERENCE, MODE_PAPER = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class NguEpiCfg(C.Structure):
@@ -53,6 +53,7 @@ SYMBOLS = {
     "ngu_epi_append": (C.c_int, [_P, _P, _P]),
     "ngu_epi_reset": (C.c_int, [_P, _P, _P]),
     "ngu_epi_step": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "ngu_epi_step_pipelined": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "ngu_epi_step_rnd": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     "ngu_epi_step_host": (C.c_int, [_P, _P, _P, _P, _P]),
     "ngu_epi_reset_host": (C.c_int, [_P, _P]),

@@ -155,6 +155,11 @@ struct EpilogueParams {
     float* log_stash;         // [2][B] r_epi, r_int of the last fused step (PH_LOGFUSE), see log_absorb
     const unsigned int* arm_go;       // pre-armed launch (ngu_epi_step_host): device word, arm_seq << 1 | cancelled once the stage
     unsigned int arm_seq;             // kernel has decided (cancelled = nobody rang the doorbell in time); 0 = not pre-armed
+    unsigned int* epi_done;   // device word: receives `seq` after this launch's last write (pipelined steps poll it)
+    unsigned int seq;         // host sequence number of this fused step; 0 = none (split sequence, graph capture)
+    unsigned int wait_prev;   // pipelined step: sequence number of the PREVIOUS fused step, whose epilogue may still be running
+                              // when this CTA starts - its stash is absorbed only once that epilogue has completed; 0 = the
+                              // previous epilogue is complete by construction (ordinary launches, see log_absorb)
     unsigned int* host_err;   // mapped host word: set to 1 when a merge / exchange timed out (sticky error, never cleared)
     unsigned int* host_flag;  // mapped host word or null: receives host_seq after the kernel's last write
     unsigned int host_seq;
@@ -355,6 +360,17 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
     // The previous fused step's reward stash -> log-only trackers, while the scan drains (see log_absorb).
     const bool logfuse = finish && (p.phases & PH_LOGFUSE) != 0;
     if (logfuse) {
+        if (p.wait_prev != 0u && threadIdx.x == 0) {
+            // Pipelined step: this CTA became resident without the scan in front of it having waited for the previous
+            // epilogue, which writes the stash and the trackers.  Wait for it here (it is resident or complete; this
+            // CTA has nothing else to do until its own scan drains).
+            unsigned int v;
+            for (int polls = 0;; ++polls) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.epi_done) : "memory");
+                if (static_cast<int>(v - p.wait_prev) >= 0) break;
+                if (polls > (1 << 22)) { atomicAdd(reinterpret_cast<unsigned long long*>(&st->exchange_timeouts), 1ull); break; }
+            }
+        }
         if (threadIdx.x == 0) s_cursor = __ldcg(&st->stash_open);      // s_cursor: scratch until the load phase
         __syncthreads();
         const bool open = s_cursor != 0;
@@ -616,11 +632,17 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
 
     EPI_STAMP(7);
     if (threadIdx.x == 0 && p.host_err && (failed_before || s_failed != 0)) *reinterpret_cast<volatile unsigned int*>(p.host_err) = 1u;
-    if (p.host_flag) {   // ngu_epi_step_host: tell the spinning host that every write of the step has been issued
+    if (p.host_flag || p.seq != 0u) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence_system();
-            *reinterpret_cast<volatile unsigned int*>(p.host_flag) = p.host_seq;
+            if (p.seq != 0u) {   // every write of this launch precedes the word a pipelined successor polls
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.epi_done), "r"(p.seq) : "memory");
+            }
+            if (p.host_flag) {   // ngu_epi_step_host: tell the spinning host that every write of the step has been issued
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned int*>(p.host_flag) = p.host_seq;
+            }
         }
     }
 }

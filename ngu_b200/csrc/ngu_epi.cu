@@ -90,17 +90,33 @@ struct ngu_epi {
     int sm_count = 0;
     bool owns_memory = false;
     float* memory = nullptr;         // [B][N][32]
-    u64* cand = nullptr;             // [B][max_cand][2] epoch-tagged candidate keys of the scan kernel
-    float* topk_d2 = nullptr;        // [B][k]
-    int32_t* topk_idx = nullptr;     // [B][k]
-    float* dist = nullptr;           // [B][k]
+    // Scan context: everything one scan launch writes and its epilogue reads.  There are two, used alternately, so
+    // that a pipelined step's scan can run while the previous step's merge tail and epilogue are still using theirs.
+    struct ScanCtx {
+        u64* cand = nullptr;             // [B][max_cand][2] epoch-tagged candidate keys of the scan kernel
+        float* topk_d2 = nullptr;        // [B][k]
+        int32_t* topk_idx = nullptr;     // [B][k]
+        float* dist = nullptr;           // [B][k]
+        u64* actor_state = nullptr;      // [B][2] per actor {published floor, arrived tiles << 32 | reserved candidates}
+        unsigned int* sched_ctr = nullptr;   // [8] dynamic chunk counter, finished-warp counter, launch epoch, merge-job counter, leftovers
+        int32_t* leftover = nullptr;     // [B] merge jobs given up by their first taker (scan_topk.cuh: merge_job)
+    } ctx[2];
+    int cur = 0;                     // context of the scan launched last
+    // fused-step chain (ngu_epi_step_pipelined)
+    bool pipe_enabled = true;        // NGU_EPI_PIPE=0: every step is launched the ordinary way (A/B)
+    bool chain_open = false;         // the last thing this handle enqueued was a fused step (eagerly, with a sequence number)
+    cudaStream_t chain_stream = nullptr;
+    unsigned int step_seq = 0;       // sequence number of the last eager fused step
+    unsigned int chain_seq = 0, chain_prev_seq = 0;   // ... of the previous one / the one before it
+    bool chain_prev_pipe = false;    // the previous fused step was launched pipelined
+    const float* chain_q = nullptr;  // its controllable states (the row its epilogue appends)
+    unsigned int* pipe_words = nullptr;   // device: [0] epi_done, [16] (64-byte offset) scan_cursor u64
+    long pipe_launches = 0;
     double* rank_sums = nullptr;     // [2k+1]
     double* log_sums = nullptr;      // [5]
     float* log_stash = nullptr;      // [2][B] rewards of the last fused step, not yet in the log-only trackers (log_absorb)
-    u64* actor_state = nullptr;              // [B][2] per actor {published floor, arrived tiles << 32 | reserved candidates}
-    unsigned int* sched_ctr = nullptr;       // [8] dynamic chunk counter, finished-warp counter, launch epoch, merge-job counter, leftovers
-    int32_t* leftover = nullptr;             // [B] merge jobs given up by their first taker (scan_topk.cuh: merge_job)
     int prefetch_tiles = 4;                  // experiments: NGU_EPI_PREFETCH_TILES
+    int l2_mode = 0; float l2_frac = 1.0f;   // L2 policy of the memory stream (ScanParams::l2_mode); NGU_EPI_L2=mode[,frac] overrides
     long long poll_limit_cycles = 4000000;   // ~2 ms without progress; NGU_EPI_DEBUG_POLL_LIMIT overrides (tests: 0)
     ScanSched sched{};
     double sched_static_frac = 0.6;          // share of the tiles handed out statically (experiments: NGU_EPI_SCHED=frac,c2)
@@ -205,6 +221,7 @@ void disarm(ngu_epi* h) {
 #endif
     }
     h->arm_misses += 1;
+    h->cur ^= 1;          // the cancelled scan never ran: the context of the last real scan is current again
 }
 // Every entry point runs on the handle's GPU and leaves the caller's current device as it found it
 // (a handle on cuda:1 must not silently switch a thread whose torch current device is cuda:0).
@@ -220,7 +237,8 @@ struct DeviceGuard {
     DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 #define BIND_DEVICE_KEEP_ARMED(h) DeviceGuard dev_guard_(h); if (dev_guard_.rc) return dev_guard_.rc
-#define BIND_DEVICE(h) BIND_DEVICE_KEEP_ARMED(h); disarm(h)
+// ... and every entry point but the fused steps themselves ends a chain of pipelined steps (they restore the flag)
+#define BIND_DEVICE(h) BIND_DEVICE_KEEP_ARMED(h); disarm(h); (h)->chain_open = false
 
 // Sticky error: once a merge or an exchange round has timed out (DevState::exchange_timeouts != 0, mirrored by
 // the epilogue into a mapped host word) every later result is wrong - the step entry points refuse to go on.
@@ -438,29 +456,37 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
         h->owns_memory = true;
         CREATE_TRY(cudaMemset(h->memory, 0, mem_bytes));                 // torch.zeros, episodic_novelty.py:32
     }
-    {   // epoch-tagged candidates: zeroed once (tag 0 is never valid), 16 bytes per entry
+    for (ngu_epi::ScanCtx& cx : h->ctx) {
+        // epoch-tagged candidates: zeroed once (tag 0 is never valid), 16 bytes per entry
         const size_t cbytes = static_cast<size_t>(B) * h->max_cand * 2 * sizeof(u64);
-        CREATE_TRY(cudaMalloc(&h->cand, cbytes));
-        CREATE_TRY(cudaMemset(h->cand, 0, cbytes));
-    }
-    CREATE_TRY(cudaMalloc(&h->topk_d2, static_cast<size_t>(B) * k * sizeof(float)));
-    CREATE_TRY(cudaMalloc(&h->topk_idx, static_cast<size_t>(B) * k * sizeof(int32_t)));
-    CREATE_TRY(cudaMalloc(&h->dist, static_cast<size_t>(B) * k * sizeof(float)));
-    CREATE_TRY(cudaMalloc(&h->rank_sums, NGU_EPI_RANK_SUMS(NGU_EPI_MAX_K) * sizeof(double)));
-    CREATE_TRY(cudaMalloc(&h->log_sums, 8 * sizeof(double)));
-    CREATE_TRY(cudaMalloc(&h->log_stash, 2 * static_cast<size_t>(cfg->n_actors) * sizeof(float)));
-    CREATE_TRY(cudaMalloc(&h->actor_state, static_cast<size_t>(B) * 2 * sizeof(u64)));
-    CREATE_TRY(cudaMemset(h->actor_state, 0, static_cast<size_t>(B) * 2 * sizeof(u64)));
-    CREATE_TRY(cudaMalloc(&h->leftover, static_cast<size_t>(B) * sizeof(int32_t)));
-    if (const char* e = getenv("NGU_EPI_DEBUG_POLL_LIMIT")) h->poll_limit_cycles = atoll(e);
-    if (const char* e = getenv("NGU_EPI_PREFETCH_TILES")) h->prefetch_tiles = atoi(e) < 0 ? 0 : (atoi(e) > kMaxPrefetchTiles ? kMaxPrefetchTiles : atoi(e));
-    CREATE_TRY(cudaMalloc(&h->sched_ctr, 8 * sizeof(unsigned int)));
-    {
+        CREATE_TRY(cudaMalloc(&cx.cand, cbytes));
+        CREATE_TRY(cudaMemset(cx.cand, 0, cbytes));
+        CREATE_TRY(cudaMalloc(&cx.topk_d2, static_cast<size_t>(B) * k * sizeof(float)));
+        CREATE_TRY(cudaMalloc(&cx.topk_idx, static_cast<size_t>(B) * k * sizeof(int32_t)));
+        CREATE_TRY(cudaMalloc(&cx.dist, static_cast<size_t>(B) * k * sizeof(float)));
+        CREATE_TRY(cudaMalloc(&cx.actor_state, static_cast<size_t>(B) * 2 * sizeof(u64)));
+        CREATE_TRY(cudaMemset(cx.actor_state, 0, static_cast<size_t>(B) * 2 * sizeof(u64)));
+        CREATE_TRY(cudaMalloc(&cx.leftover, static_cast<size_t>(B) * sizeof(int32_t)));
+        CREATE_TRY(cudaMalloc(&cx.sched_ctr, 8 * sizeof(unsigned int)));
         unsigned int init[8] = {0u, 0u, 1u, 0u, 0u, 0u, 0u, 0u};   // first launch epoch = 1
         if (const char* e = getenv("NGU_EPI_DEBUG_EPOCH")) init[2] = static_cast<unsigned int>(strtoul(e, nullptr, 0));   // tests: cross the wrap
         if (init[2] == 0u) init[2] = 1u;
-        CREATE_TRY(cudaMemcpy(h->sched_ctr, init, sizeof init, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(cx.sched_ctr, init, sizeof init, cudaMemcpyHostToDevice));
     }
+    CREATE_TRY(cudaMalloc(&h->pipe_words, 256));
+    CREATE_TRY(cudaMemset(h->pipe_words, 0, 256));
+    if (const char* e = getenv("NGU_EPI_PIPE")) h->pipe_enabled = atoi(e) != 0;
+    CREATE_TRY(cudaMalloc(&h->rank_sums, NGU_EPI_RANK_SUMS(NGU_EPI_MAX_K) * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->log_sums, 8 * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->log_stash, 2 * static_cast<size_t>(cfg->n_actors) * sizeof(float)));
+    if (const char* e = getenv("NGU_EPI_DEBUG_POLL_LIMIT")) h->poll_limit_cycles = atoll(e);
+    if (const char* e = getenv("NGU_EPI_L2")) {
+        int m = 0; float f = 1.0f;
+        const int got = sscanf(e, "%d,%f", &m, &f);
+        if (got >= 1 && m >= 0 && m <= 2) h->l2_mode = m;
+        if (got >= 2 && f > 0.0f && f <= 1.0f) h->l2_frac = f;
+    }
+    if (const char* e = getenv("NGU_EPI_PREFETCH_TILES")) h->prefetch_tiles = atoi(e) < 0 ? 0 : (atoi(e) > kMaxPrefetchTiles ? kMaxPrefetchTiles : atoi(e));
     CREATE_TRY(cudaMalloc(&h->state, sizeof(DevState)));
     CREATE_TRY(cudaMemset(h->state, 0, sizeof(DevState)));
     {
@@ -546,8 +572,12 @@ void ngu_epi_destroy(ngu_epi* h) {
             if (g != h->p2p.rank && h->p2p.peer[g]) cudaIpcCloseMemHandle(h->p2p.peer[g]);
     cudaFree(h->inbox);
     if (h->owns_memory) cudaFree(h->memory);
-    cudaFree(h->cand); cudaFree(h->topk_d2); cudaFree(h->topk_idx); cudaFree(h->dist);
-    cudaFree(h->rank_sums); cudaFree(h->log_sums); cudaFree(h->log_stash); cudaFree(h->state); cudaFree(h->actor_state); cudaFree(h->sched_ctr); cudaFree(h->leftover); cudaFree(h->plan_dev); cudaFree(h->timeline); cudaFree(h->epi_stamps);
+    for (ngu_epi::ScanCtx& cx : h->ctx) {
+        cudaFree(cx.cand); cudaFree(cx.topk_d2); cudaFree(cx.topk_idx); cudaFree(cx.dist);
+        cudaFree(cx.actor_state); cudaFree(cx.sched_ctr); cudaFree(cx.leftover);
+    }
+    cudaFree(h->pipe_words);
+    cudaFree(h->rank_sums); cudaFree(h->log_sums); cudaFree(h->log_stash); cudaFree(h->state); cudaFree(h->plan_dev); cudaFree(h->timeline); cudaFree(h->epi_stamps);
     cudaFree(h->q_stage_dev); cudaFree(h->done_stage_dev); cudaFree(h->arm_cancel_dev);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->r_mapped) cudaFreeHost(h->r_mapped);
@@ -580,19 +610,28 @@ static cudaError_t launch_pdl(const void* fn, dim3 grid, dim3 block, size_t smem
     return cudaLaunchKernelExC(&cfg, fn, args);
 }
 
-static int launch_scan(ngu_epi* h, const float* q_dev, cudaStream_t s) {
+// Sequence numbers of a fused step's launches (all zero: a launch outside any chain - split sequence, RND step, capture).
+struct ChainArgs { unsigned int seq = 0, prev_seq = 0, wait_epi = 0; bool pipe = false; const float* q_prev = nullptr; };
+
+static int launch_scan(ngu_epi* h, const float* q_dev, cudaStream_t s, const ChainArgs& ca = ChainArgs{}) {
     if (reinterpret_cast<uintptr_t>(q_dev) & 15u)   // the scan fetches query rows with 16-byte bulk copies
         return fail(h, NGU_EINVAL, "q_dev must be 16-byte aligned");
+    h->cur ^= 1;                                    // the other context: the previous step may still be using its own
+    const ngu_epi::ScanCtx& cx = h->ctx[h->cur];
     ScanParams sp{};
-    sp.q = q_dev; sp.cand = h->cand;
+    sp.pipe = ca.pipe ? 1 : 0; sp.seq = ca.seq; sp.prev_seq = ca.prev_seq; sp.wait_epi = ca.wait_epi; sp.q_prev = ca.q_prev;
+    sp.epi_done = h->pipe_words; sp.scan_cursor = reinterpret_cast<unsigned long long*>(h->pipe_words + 16);
+    sp.cursor = &h->state->cursor;
+    sp.q = q_dev; sp.cand = cx.cand;
     sp.n_actors = h->cfg.n_actors; sp.capacity = h->cfg.capacity; sp.k = h->cfg.k;
     sp.largest = h->consts.largest; sp.sqrt_dist = h->consts.sqrt_dist; sp.neg_zero2 = kNegZero2;
     sp.tiles_per_actor = h->tiles_per_actor;
-    sp.max_cand = h->max_cand; sp.sched = h->sched; sp.sched_ctr = h->sched_ctr;
-    sp.leftover = h->leftover; sp.poll_limit_cycles = h->poll_limit_cycles; sp.prefetch_tiles = h->prefetch_tiles;
-    sp.actor_state = h->actor_state;
+    sp.max_cand = h->max_cand; sp.sched = h->sched; sp.sched_ctr = cx.sched_ctr;
+    sp.leftover = cx.leftover; sp.poll_limit_cycles = h->poll_limit_cycles; sp.prefetch_tiles = h->prefetch_tiles;
+    sp.l2_mode = h->l2_mode; sp.l2_frac = h->l2_frac;
+    sp.actor_state = cx.actor_state;
     sp.timeouts = reinterpret_cast<unsigned long long*>(&h->state->exchange_timeouts);
-    sp.topk_d2 = h->topk_d2; sp.topk_idx = h->topk_idx; sp.dist = h->dist;
+    sp.topk_d2 = cx.topk_d2; sp.topk_idx = cx.topk_idx; sp.dist = cx.dist;
     sp.timeline = h->timeline;
     sp.arm_go = h->arm_cancel_dev; sp.arm_seq = h->arm_seq_next;
     sp.debug = h->debug_scan;
@@ -610,14 +649,15 @@ struct HostFlag { unsigned int* flag; unsigned int seq; };
 
 static int launch_epilogue(ngu_epi* h, int phases, const double* sums_in, const float* alpha, float* r_int,
                            float* r_epi, double* log_sums, const float* q, cudaStream_t s,
-                           const RndArgs* rnd = nullptr, const HostFlag* hf = nullptr) {
+                           const RndArgs* rnd = nullptr, const HostFlag* hf = nullptr, const ChainArgs& ca = ChainArgs{}) {
     EpilogueParams ep{};
+    ep.epi_done = h->pipe_words; ep.seq = ca.seq; ep.wait_prev = ca.pipe ? ca.prev_seq : 0u;
     if (hf) { ep.host_flag = hf->flag; ep.host_seq = hf->seq; }
     ep.host_err = h->err_mapped_dev;
     ep.arm_go = h->arm_cancel_dev; ep.arm_seq = h->arm_seq_next;
     ep.dbg_stamps = h->epi_stamps;
     if (rnd) { ep.rnd_pred = rnd->pred; ep.rnd_targ = rnd->targ; ep.alpha_out = rnd->alpha_out; }
-    ep.dist = h->dist; ep.rank_sums = h->rank_sums; ep.sums_in = sums_in; ep.alpha = alpha;
+    ep.dist = h->ctx[h->cur].dist; ep.rank_sums = h->rank_sums; ep.sums_in = sums_in; ep.alpha = alpha;
     ep.r_int = r_int; ep.r_epi = r_epi; ep.log_sums = log_sums; ep.q = q; ep.memory = h->memory;
     ep.state = h->state; ep.phases = phases & h->debug_phase_mask;
     if (h->p2p_connected && (phases & PH_FINISH) && (phases & PH_RANKSUMS)) {   // fused single-launch step only
@@ -705,14 +745,39 @@ int ngu_epi_reset(ngu_epi* h, const uint8_t* done_dev, void* stream) {
     return NGU_OK;
 }
 
+// One fused step.  `pipelined`: the caller asked for ngu_epi_step_pipelined AND the chain was open when it entered, i.e.
+// the previous thing this handle enqueued was a fused step; everything else is decided here.
 static int step_impl(ngu_epi* h, const float* q_dev, const float* alpha_dev, float* r_int_dev, float* r_epi_dev,
-                     cudaStream_t s, const HostFlag* hf) {
-    int rc = launch_scan(h, q_dev, s);
+                     cudaStream_t s, const HostFlag* hf, bool pipelined = false) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+    const bool capturing = cap != cudaStreamCaptureStatusNone;   // a graph replays frozen arguments: no sequence numbers
+    ChainArgs ca;
+    if (!capturing) {
+        ca.seq = ++h->step_seq;
+        if (ca.seq == 0u) ca.seq = ++h->step_seq;
+    }
+    const bool timed = h->t_used < h->t_beg.size();
+    if (pipelined && !capturing && !timed && h->pipe_enabled && h->use_pdl && h->chain_stream == s && h->chain_seq != 0u) {
+        ca.pipe = true;
+        ca.prev_seq = h->chain_seq;
+        ca.wait_epi = h->chain_prev_pipe ? h->chain_prev_seq : 0u;
+        ca.q_prev = h->chain_q;
+        h->pipe_launches += 1;
+    }
+    int rc = launch_scan(h, q_dev, s, ca);
     if (rc) return rc;
     // one epilogue launch: rank sums -> running-mean update -> rewards (stashed for the log-only trackers, which the
     // next fused launch brings up to date: epilogue.cuh, log_absorb) -> append
-    return launch_epilogue(h, PH_RANKSUMS | PH_FINISH | PH_APPEND | PH_LOGFUSE, nullptr, alpha_dev, r_int_dev,
-                           r_epi_dev, nullptr, q_dev, s, nullptr, hf);
+    rc = launch_epilogue(h, PH_RANKSUMS | PH_FINISH | PH_APPEND | PH_LOGFUSE, nullptr, alpha_dev, r_int_dev,
+                         r_epi_dev, nullptr, q_dev, s, nullptr, hf, ca);
+    if (rc) return rc;
+    h->chain_open = ca.seq != 0u;
+    h->chain_stream = s;
+    h->chain_prev_seq = h->chain_seq; h->chain_seq = ca.seq;
+    h->chain_prev_pipe = ca.pipe;
+    h->chain_q = q_dev;
+    return NGU_OK;
 }
 
 int ngu_epi_step(ngu_epi* h, const float* q_dev, const float* alpha_dev, float* r_int_dev, float* r_epi_dev,
@@ -723,6 +788,17 @@ int ngu_epi_step(ngu_epi* h, const float* q_dev, const float* alpha_dev, float* 
     if (rc) return rc;
     note_user_stream(h, static_cast<cudaStream_t>(stream));
     return step_impl(h, q_dev, alpha_dev, r_int_dev, r_epi_dev, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int ngu_epi_step_pipelined(ngu_epi* h, const float* q_dev, const float* alpha_dev, float* r_int_dev, float* r_epi_dev,
+                           void* stream) {
+    if (!h || !q_dev || !r_int_dev) return fail(h, NGU_EINVAL, "null argument");
+    const bool chain_was_open = h->chain_open;
+    BIND_DEVICE(h);
+    const int rc = check_sticky(h);
+    if (rc) return rc;
+    note_user_stream(h, static_cast<cudaStream_t>(stream));
+    return step_impl(h, q_dev, alpha_dev, r_int_dev, r_epi_dev, static_cast<cudaStream_t>(stream), nullptr, chain_was_open);
 }
 
 int ngu_epi_step_rnd(ngu_epi* h, const float* q_dev, const float* pred_dev, const float* targ_dev, int32_t feat_dim,
@@ -793,6 +869,7 @@ int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host, 
                       float* r_epi_host) {
     if (!h || !q_host || !r_int_host) return fail(h, NGU_EINVAL, "null argument");
     BIND_DEVICE_KEEP_ARMED(h);
+    h->chain_open = false;
     int rc = check_sticky(h);
     if (rc) return rc;
     using clk = std::chrono::steady_clock;
@@ -829,7 +906,7 @@ int ngu_epi_step_host(ngu_epi* h, const float* q_host, const float* alpha_host, 
 #endif
         }
         running = (v & 1u) == 0u;
-        if (running) h->arm_hits += 1; else h->arm_misses += 1;
+        if (running) h->arm_hits += 1; else { h->arm_misses += 1; h->cur ^= 1; }   // (cancelled: its scan context was never used)
     } else if (h->armed_seq != 0u) {
         disarm(h);                               // (cannot happen: armed steps are always the next sequence number)
     }
@@ -903,8 +980,8 @@ int ngu_epi_topk_host(ngu_epi* h, float* d2_host, int32_t* idx_host) {
     BIND_DEVICE(h);
     CU_TRY(h, cudaDeviceSynchronize());
     const size_t n = static_cast<size_t>(h->cfg.n_actors) * h->cfg.k;
-    CU_TRY(h, cudaMemcpy(d2_host, h->topk_d2, n * sizeof(float), cudaMemcpyDeviceToHost));
-    CU_TRY(h, cudaMemcpy(idx_host, h->topk_idx, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CU_TRY(h, cudaMemcpy(d2_host, h->ctx[h->cur].topk_d2, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CU_TRY(h, cudaMemcpy(idx_host, h->ctx[h->cur].topk_idx, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return NGU_OK;
 }
 

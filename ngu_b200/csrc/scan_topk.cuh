@@ -117,6 +117,10 @@ struct ScanParams {
                                    // merge jobs (all zero between launches), [2] launch epoch = tag of this launch's
                                    // candidates and floors (never 0)
     int32_t prefetch_tiles;        // tiles per warp prefetched into L2 before the grid dependency resolves
+    int32_t l2_mode;               // L2 eviction policy of the memory stream: 0 evict_first (read once per step, much larger
+    float l2_frac;                 // than L2), 1 evict_normal, 2 evict_last for a fraction l2_frac of the lines (by address
+                                   // hash: the same lines every step), rest evict_first.  Experiment knob (NGU_EPI_L2):
+                                   // measured, no gain even for sets that fit the L2 ("Measured and rejected")
     int32_t* leftover;             // [B] actors whose merge job was given up (see merge_job), merged by the last warp
     long long poll_limit_cycles;   // a merge job that sees no progress for this long is given up (0: at once - tests)
     unsigned long long* timeouts;  // incremented if a merge gave up waiting for a candidate (must stay 0)
@@ -126,6 +130,17 @@ struct ScanParams {
     float* topk_d2;          // [B][k]
     int32_t* topk_idx;       // [B][k]
     float* dist;             // [B][k]
+    // ---- pipelined step (ngu_epi_step_pipelined; see "software pipeline over steps" at the kernel's start) ----
+    int32_t pipe;                     // 1: this launch does NOT wait for the previous step's epilogue before it streams
+    uint32_t seq;                     // host sequence number of this fused step (never 0; 0 = split sequence / graph capture:
+                                      // the launch takes no part in the cursor chain)
+    uint32_t prev_seq;                // pipe: sequence number of the previous fused step (whose epilogue may still be running)
+    uint32_t wait_epi;                // pipe: epilogue sequence number that must have completed before this launch touches
+                                      // anything (the step before the previous one, if the previous one was pipelined too); 0 = none
+    const unsigned int* epi_done;     // device word: sequence number of the last completed fused epilogue
+    unsigned long long* scan_cursor;  // device word: seq << 32 | ring slot that step `seq` appends to, published by every scan
+    const long long* cursor;          // DevState::cursor (exact once the predecessor has completed: ordinary launches)
+    const float* q_prev;              // pipe: [B][32] the previous step's controllable states = what its epilogue is appending
     const unsigned int* arm_go;       // pre-armed launch (ngu_epi_step_host, see armed_stage_kernel): device word the stage kernel
     unsigned int arm_seq;             // sets to arm_seq << 1 | cancelled when the step's inputs are in place (or the step is
                                       // cancelled); arm_seq == 0: an ordinary launch
@@ -584,6 +599,20 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+// Experiment knob: working sets that (partly) fit the 126 MB L2 - a strong-scaling shard of 32 actors x 30k is 123 MB -
+// could stay resident across steps: evict_normal, or a FIXED fraction of the lines evict_last (picked by address, so
+// the same lines every step).  Measured: no gain (tools/l2_sweep.py; DESIGN.md, "Measured and rejected").
+__device__ __forceinline__ uint64_t l2_stream_policy(int mode, float frac) {
+    uint64_t pol;
+    if (mode == 1) {
+        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    } else if (mode == 2) {
+        asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol) : "f"(frac));
+    } else {
+        pol = l2_evict_first_policy();
+    }
+    return pol;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0,
                                             int32_t c1, uint32_t bar, uint64_t policy) {
     asm volatile(
@@ -664,7 +693,8 @@ struct ScanCfg {
     static constexpr int kTileRows = 32 * RPL;
     static constexpr int kTileBytes = kTileRows * 128;
     static constexpr int kThreads = WARPS * 32;
-    static constexpr int kAuxBytes = 128 + 16;   // per stage: query row + {floor, ctr} of the actor whose run starts there
+    static constexpr int kAuxBytes = 128 + 16 + 128;   // per stage: query row + {floor, ctr} of the actor whose run starts there
+                                                       // + the row the previous step is appending (pipelined launches)
     // tiles + 1024 B alignment slack + barriers + per-stage descriptors + per-stage run-start data
     static constexpr int kSmemBytes = WARPS * STAGES * kTileBytes + 1024 + WARPS * STAGES * (16 + kAuxBytes);
     // CTAs per SM the shared memory allows (227 KB per SM): tells ptxas how many registers it may use.
@@ -725,7 +755,60 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
         }
     }
     __syncwarp();
-    pdl_wait();   // predecessor (previous step's epilogue: append, readers of dist/topk) is complete
+    // ---- software pipeline over steps (p.pipe, ngu_epi_step_pipelined) ------------------------------------------
+    // Step s+1's scan depends on step s only through ONE row per actor: the slot c(s) that epilogue s appends q(s)
+    // to.  A pipelined launch therefore does not wait for its predecessor at all: it streams while the previous
+    // scan's merge tail, the previous epilogue and (multi-GPU) its NVLink exchange are still running, and takes the
+    // content of row c(s) from q(s) itself (q_prev: an extra 128-byte bulk copy that rides on the tile's mbarrier and
+    // replaces that row of the tile, whatever state the append is in).  c(s) comes from a word every scan publishes
+    // before it lets its dependents start (scan_cursor = seq << 32 | slot): an ordinary launch reads the exact device
+    // cursor after its grid dependency has resolved, a pipelined one advances the previous launch's value.
+    // Two steps deep, no more: this launch works on the scan context (candidates, counters, k-NN outputs) that step
+    // s-1 used, so it first waits for epilogue s-1 (wait_epi, normally long complete); all of its predecessors' CTAs
+    // are resident by construction (a kernel only becomes resident after ALL CTAs of its primary have signalled), so
+    // nothing it polls can be waiting for an SM.  Before a warp exits it executes griddepcontrol.wait, so that the
+    // completion of this grid still implies the completion of everything before it (the epilogues stay ordered).
+    int hz_tile = -1, hz_row = 0;      // tile-in-actor / row-in-tile of the slot being appended (none: -1)
+    bool chained = false;
+    if (p.pipe) {
+        u64 w = 0ull;
+        if (lane == 0) {
+            if (p.wait_epi != 0u) {
+                unsigned int v;
+                int polls = 0;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.epi_done) : "memory");
+                    if (static_cast<int>(v - p.wait_epi) >= 0) break;
+                    if (++polls > kLLSpinLimit) { atomicAdd(p.timeouts, 1ull); break; }
+                }
+            }
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p.scan_cursor) : "memory");
+        }
+        w = __shfl_sync(kFull, w, 0);
+        const uint32_t ws = static_cast<uint32_t>(w >> 32);
+        const int c = static_cast<int>(static_cast<uint32_t>(w));
+        int row = -1;
+        if (ws == p.prev_seq) row = c;                          // the previous step's slot
+        else if (ws == p.seq) row = c == 0 ? N - 1 : c - 1;     // CTA 0 of this launch has already advanced the word
+        if (row >= 0 && row < N) {
+            chained = true;
+            hz_tile = row / Cfg::kTileRows;
+            hz_row = row - hz_tile * Cfg::kTileRows;
+            if (gw == 0 && lane == 0 && ws == p.prev_seq) {
+                const u64 nw = (static_cast<u64>(p.seq) << 32) | static_cast<u64>(row + 1 == N ? 0 : row + 1);
+                asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p.scan_cursor), "l"(nw) : "memory");
+                __threadfence();
+            }
+        }
+    }
+    if (!chained) {
+        pdl_wait();   // predecessor (previous step's epilogue: append, readers of dist/topk) is complete
+        if (p.seq != 0u && gw == 0 && lane == 0) {              // head of a chain: the exact cursor
+            const u64 nw = (static_cast<u64>(p.seq) << 32) | static_cast<u64>(__ldcg(p.cursor));
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p.scan_cursor), "l"(nw) : "memory");
+            __threadfence();
+        }
+    }
     // A pre-armed step (ngu_epi_step_host, armed_stage_kernel) whose doorbell never rang: leave without touching
     // anything (the exit releases the epilogue behind us, which does the same).
     // (Measured and rejected: polling this word for "go" instead of waiting for the stage kernel to exit.  With
@@ -737,7 +820,7 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
     // our CTAs exits (shared memory) or, on small grids, has tens of microseconds of streaming left to do so.
     pdl_launch_dependents();
 
-    const uint64_t policy = l2_evict_first_policy();
+    const uint64_t policy = l2_stream_policy(p.l2_mode, p.l2_frac);
     const uint32_t tag = __ldcg(p.sched_ctr + 2);   // launch epoch (first needed at the first flush)
 
     // ---- producer (lane 0): walks this warp's chunks STAGES tiles ahead of the consumer ----
@@ -761,14 +844,16 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
             asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(dsc), "r"(pb), "r"(pti) : "memory");
             const uint32_t bar = my_bars + 8 * s;
             const bool run_start = pb != last_pb;
-            mbar_expect_tx(bar, Cfg::kTileBytes + (run_start ? Cfg::kAuxBytes : 0));
+            const bool hz = pti == hz_tile;   // pipelined launch: the tile holds the slot the previous step is appending to
+            mbar_expect_tx(bar, Cfg::kTileBytes + (run_start ? 144 : 0) + (hz ? 128 : 0));
             tma_load_2d(my_tiles + s * Cfg::kTileBytes, &tmap, 0, pb * N + pti * Cfg::kTileRows, bar, policy);
+            const uint32_t aux = my_aux + s * Cfg::kAuxBytes;
             if (run_start) {           // the run's query row and floor travel with its first tile
-                const uint32_t aux = my_aux + s * Cfg::kAuxBytes;
                 bulk_load(aux, p.q + static_cast<int64_t>(pb) * 32, 128, bar);
                 bulk_load(aux + 128, actor_floor(p, pb), 16, bar);
                 last_pb = pb;
             }
+            if (hz) bulk_load(aux + 144, p.q_prev + static_cast<int64_t>(pb) * 32, 128, bar);   // that slot's final content
             ++pt;
             if (++pti == tpa) { pti = 0; ++pb; }
         } else {
@@ -840,9 +925,16 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
 #pragma unroll
             for (int i = 0; i < RPL; ++i) d2[i] = lds128(tile + static_cast<uint32_t>(lane + 32 * i) * 128u + (sw << 4)).x;
         } else {
+            const bool hz = ti == hz_tile;
 #pragma unroll
-            for (int i = 0; i < RPL; ++i)
-                d2[i] = row_d2(tile + static_cast<uint32_t>(lane + 32 * i) * 128u, sw, q, p.neg_zero2);
+            for (int i = 0; i < RPL; ++i) {
+                uint32_t ra = tile + static_cast<uint32_t>(lane + 32 * i) * 128u, rs = sw;
+                if (hz && lane + 32 * i == hz_row) {   // the slot being appended: its content from q_prev (linear, not swizzled)
+                    ra = my_aux + stage * Cfg::kAuxBytes + 144;
+                    rs = 0u;
+                }
+                d2[i] = row_d2(ra, rs, q, p.neg_zero2);
+            }
         }
         __syncwarp();  // every lane is done reading this slot (and has read its descriptor)
 
@@ -885,6 +977,7 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
         }
     }
     else if (top.lkey == 0x1234567ull) p.topk_d2[0] = 0.f;   // keep the experiment's loads alive
+    if (chained) pdl_wait();   // pipelined launch: this grid must not complete before its predecessors have
     // The last working warp of the launch merges the jobs that were given up (normally none) and re-arms the
     // scheduler for the next launch (every other warp has consumed the result of its last counter atomic
     // before it got here).

@@ -148,16 +148,25 @@ class EpisodicEngine:
         self._done_keep = done
         check(self._lib.ngu_epi_reset(self._h, _ptr(done), self._stream()), self._h)
 
-    def step(self, q: torch.Tensor, alpha: torch.Tensor | None = None):
-        """scan -> finish -> append on the current stream; returns device tensors (r_int, r_epi)."""
+    def step(self, q: torch.Tensor, alpha: torch.Tensor | None = None, pipelined: bool = False, out=None):
+        """scan -> finish -> append on the current stream; returns device tensors (r_int, r_epi).
+
+        ``pipelined=True`` (ngu_epi_step_pipelined): for steps enqueued back to back whose inputs are already on the
+        device.  The step's scan overlaps the previous step's merge tail / epilogue / exchange; same results, bit
+        for bit.  Contract (include/ngu_epi.h): nothing else was enqueued on the stream since the previous step,
+        this step's q / alpha were ready before the previous step was enqueued, and the previous step's q stays
+        intact until this step has completed (the engine keeps a reference to it for that long).
+        ``out=(r_int, r_epi)``: write the rewards there instead of the engine's own pair of buffers."""
         self._version += 1
-        self._q_keep = self._q(q)
+        qk = self._q(q)
         if alpha is not None:
             alpha = alpha.to(device=self.device, dtype=torch.float32).contiguous()
-        self._alpha_keep = alpha
-        check(self._lib.ngu_epi_step(self._h, _ptr(self._q_keep), _ptr(alpha), _ptr(self._r_int), _ptr(self._r_epi),
-                                     self._stream()), self._h)
-        return self._r_int, self._r_epi
+        r_int, r_epi = out if out is not None else (self._r_int, self._r_epi)
+        fn = self._lib.ngu_epi_step_pipelined if pipelined else self._lib.ngu_epi_step
+        check(fn(self._h, _ptr(qk), _ptr(alpha), _ptr(r_int), _ptr(r_epi), self._stream()), self._h)
+        self._q_keep2, self._q_keep = getattr(self, "_q_keep", None), qk      # the previous q outlives this step
+        self._alpha_keep2, self._alpha_keep = getattr(self, "_alpha_keep", None), alpha
+        return r_int, r_epi
 
     def step_rnd(self, q: torch.Tensor, pred: torch.Tensor, targ: torch.Tensor):
         """ngu_epi_step_rnd: RND features in, the modulator is computed inside the epilogue kernel.

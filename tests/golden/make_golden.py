@@ -75,6 +75,8 @@ CASES = [
     ("scale_50",                5, 300, 25, 19, 50.0, 0.0, "randn", "randn"),
     ("b64_n5000",              64, 5000, 6, 20, 1.0, 0.0, "randn", "randn"),
     ("b256_n300",             256, 300, 8, 21, 1.0, 0.01, "randn", "randn"),
+    # the headline shape itself (BASELINE.json configs[2]): two recorded steps, the 983 MB prefill is rebuilt from the seed
+    ("b256_n30000",           256, 30000, 2, 22, 1.0, 0.0, "randn", "randn"),
 ]
 
 
@@ -156,6 +158,88 @@ def run_case(torch, IntrinsicNovelty, model_hypr, name, B, N, steps, seed, scale
     print(f"{name}: B={B} N={N} steps={steps} reward[0,:3]={out['reward'][0, :3]}")
 
 
+# ---- the real-CNN drop-in: Embedding + RND stacks in front of the scan --------------------------------
+CNN_CASE = dict(B=8, N=256, steps=16, seed=31, mem_scale=2.0)
+
+
+def fill_cnn_weights(module, seed):
+    """Deterministic weights for a CNN stack from numpy's PCG64 (platform independent, and the same call fills the
+    reference's modules here and the drop-in's modules in the GPU test: their state_dict keys and shapes agree).
+    Weights ~ N(0, 2 / fan_in), biases ~ N(0, 0.05^2): activations stay O(1) through the four layers."""
+    import torch
+    rng = np.random.default_rng(seed)
+    sd = module.state_dict()
+    for name in sorted(sd):
+        t = sd[name]
+        if not torch.is_floating_point(t):
+            continue
+        if t.dim() >= 2:
+            fan_in = int(np.prod(t.shape[1:]))
+            w = rng.standard_normal(tuple(t.shape)).astype(np.float32) * np.float32(np.sqrt(2.0 / fan_in))
+        else:
+            w = rng.standard_normal(tuple(t.shape)).astype(np.float32) * np.float32(0.05)
+        t.copy_(torch.from_numpy(w))
+    return module
+
+
+def cnn_observations(B, steps, seed):
+    """Synthetic observations [steps,B,1,84,84]: N(0,1) clipped to +-5, what VecNormalize hands the agent
+    (envs/utils.py:37, atari_env_hypr.py:13)."""
+    rng = np.random.default_rng(seed + 500)
+    return np.clip(rng.standard_normal((steps, B, 1, 84, 84), dtype=np.float32), -5.0, 5.0)
+
+
+def run_cnn_case(torch, IntrinsicNovelty, model_hypr):
+    """Golden for the whole drop-in call on OBSERVATIONS: the unmodified reference IntrinsicNovelty with its real
+    Embedding and RND networks (fixed weights), CPU float32.  Recorded per step: the reference's embeddings
+    (embedding.py:48-49), the RND modulator (lifelong_novelty.py:49-57), the returned intrinsic reward
+    (intrinsic_novelty.py:20-34), and the k+1 largest d^2 with their canonical slots (the (k+1)-th is recorded so
+    that a test can tell which rank orders are separated by more than the embedding error)."""
+    B, N, steps, seed = (CNN_CASE[x] for x in ("B", "N", "steps", "seed"))
+    hy = dict(model_hypr, episodic_memory_capacity=N)
+    k = hy["num_neighbors"]
+    torch.manual_seed(seed)
+    inn = IntrinsicNovelty(B, 18, (1, 84, 84), hy, _NullLogger())
+    with torch.no_grad():
+        fill_cnn_weights(inn.epi_novel.embedding, seed + 1)
+        fill_cnn_weights(inn.ll_novel.predictor, seed + 2)
+        fill_cnn_weights(inn.ll_novel.target, seed + 3)
+    en = inn.epi_novel
+    # memory prefilled at the embeddings' scale (|q| ~ 10): with an empty memory every neighbour is a zero slot
+    en.episodic_memory = torch.from_numpy(prefill_memory("randn", N, B, seed, CNN_CASE["mem_scale"]).copy())
+    obs = cnn_observations(B, steps, seed)
+    rec = {k_: [] for k_ in ("emb", "alpha", "reward", "d2", "idx", "ll_rms", "ed_mean")}
+    real_ll = inn.ll_novel.compute_lifelong_curiosity
+    for t in range(steps):
+        o = torch.from_numpy(obs[t])
+        with torch.no_grad():
+            q = en.embedding(o).detach()
+        d2_all = ((en.episodic_memory - q.unsqueeze(0)) ** 2).sum(dim=-1)
+        canon = torch.sort(d2_all, dim=0, descending=True, stable=True)
+        seen = {}
+        def spy(x, seen=seen):
+            seen["alpha"] = real_ll(x)
+            return seen["alpha"].clone()
+        inn.ll_novel.compute_lifelong_curiosity = spy
+        out = inn.compute_intrinsic_novelty(o)                 # THE reference call, real CNNs
+        rec["emb"].append(q.numpy().copy())
+        rec["alpha"].append(seen["alpha"].numpy().astype(np.float64).copy())
+        rec["reward"].append(out.numpy()[:, 0].astype(np.float64))
+        rec["d2"].append(canon.values[:k + 1].numpy().copy())
+        rec["idx"].append(canon.indices[:k + 1].numpy().astype(np.int32))
+        rec["ll_rms"].append(np.array([float(inn.ll_novel.ll_rms.mean), float(inn.ll_novel.ll_rms.var),
+                                       float(inn.ll_novel.ll_rms.count)], np.float64))
+        rec["ed_mean"].append(np.broadcast_to(en.ed_rms.mean, (k,)).astype(np.float64).copy())
+    out = {k_: np.stack(v) for k_, v in rec.items()}
+    out["mem_final"] = en.episodic_memory.numpy().copy()
+    out["meta"] = np.array([B, N, k, steps, seed], dtype=np.int64)
+    out["versions"] = np.array([f"torch {torch.__version__}", f"numpy {np.__version__}"])
+    os.makedirs(os.path.join(HERE, "..", "golden_cnn"), exist_ok=True)
+    np.savez_compressed(os.path.join(HERE, "..", "golden_cnn", "dropin_cnn.npz"), **out)
+    print(f"dropin_cnn: B={B} N={N} steps={steps} |emb| ~ {np.abs(out['emb']).mean():.3f} alpha[-1,:3]={out['alpha'][-1, :3]} "
+          f"reward[-1,:3]={out['reward'][-1, :3]}")
+
+
 def rnd_features(B, steps):
     """Synthetic RND (predictor, target) features [steps,B,128] from numpy's platform-independent PCG64."""
     rng = np.random.default_rng(3100 + B)
@@ -208,10 +292,15 @@ def lane8_probe(torch):
 def main():
     torch, IntrinsicNovelty, model_hypr = _import_reference()
     lane8_probe(torch)
+    only = sys.argv[1:]                       # optional: names of the cases to (re)generate
     for case in CASES:
-        run_case(torch, IntrinsicNovelty, model_hypr, *case)
-    os.makedirs(os.path.join(HERE, "..", "golden_rnd"), exist_ok=True)
-    run_rnd_case(torch, model_hypr)
+        if not only or case[0] in only:
+            run_case(torch, IntrinsicNovelty, model_hypr, *case)
+    if not only or "rnd_tail" in only:
+        os.makedirs(os.path.join(HERE, "..", "golden_rnd"), exist_ok=True)
+        run_rnd_case(torch, model_hypr)
+    if not only or "dropin_cnn" in only:
+        run_cnn_case(torch, IntrinsicNovelty, model_hypr)
 
 
 if __name__ == "__main__":

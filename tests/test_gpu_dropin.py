@@ -186,3 +186,101 @@ def test_collect_sequence_style_loop_300_steps(cuda_device):
     assert n_resets > 100 and inn.epi_novel.memory_idx == steps % N
     assert np.array_equal(inn.epi_novel.episodic_memory.cpu().numpy(), orc.memory)
     assert inn.epi_novel.ed_rms.count == k + steps * B
+
+
+# ---- the real-CNN drop-in against the reference run on OBSERVATIONS -----------------------------------
+# tests/golden_cnn/dropin_cnn.npz is recorded by tests/golden/make_golden.py::run_cnn_case from the unmodified
+# reference IntrinsicNovelty (real Embedding + RND stacks, fixed PCG64 weights, CPU float32).  The GPU runs the same
+# weights through cuDNN / cuBLAS in float32 with TF32 switched OFF; the two conv implementations sum in different
+# orders, so the embeddings agree to float32 rounding accumulated over four layers, not bit for bit.  Tolerances
+# (measured on a B200 with margin, tools/cnn_dropin_probe.py):
+CNN_EMB_ATOL = 2e-5        # |embedding - reference|, embeddings are O(1) (mean |q_d| = 1.3); measured 8.9e-6
+CNN_D2_RTOL = 5e-6         # k-NN d^2 values; measured 7.5e-7
+CNN_ALPHA_ATOL = 5e-5      # RND modulator 1 + (err - mean) / sqrt(var): amplifies the feature error by 1 / std(err); measured 8.9e-6
+CNN_REWARD_RTOL = 2e-5     # r_int = r_epi * clip(alpha, 1, 5) inherits alpha's error where 1 < alpha < 5; measured 5.7e-6
+CNN_REPI_RTOL = 1e-5       # ... the episodic part alone meets north_star's 1e-5; measured 1.3e-7
+# Slot rule: the reference's rank order between neighbours j and j+1 is DECIDED when their d^2 differ by more than
+# CNN_GAP relative (20x CNN_D2_RTOL, 130x the measured d^2 error); an actor-step is compared slot by slot when all k
+# gaps of its reference top-(k+1) are decided and skipped otherwise (123 of the golden's 128 actor-steps are decided).
+CNN_GAP = 1e-4
+
+
+def _cnn_dropin(hy):
+    import ngu_b200.pytorch_util as ptu
+    from ngu_b200.intrinsic_novelty import IntrinsicNovelty
+    from tests.golden.make_golden import CNN_CASE, fill_cnn_weights, prefill_memory
+    ptu.init_device()
+    B, N, seed = CNN_CASE["B"], CNN_CASE["N"], CNN_CASE["seed"]
+    inn = IntrinsicNovelty(B, 18, (1, 84, 84), dict(hy, episodic_memory_capacity=N), _NullLogger())
+    with torch.no_grad():
+        fill_cnn_weights(inn.epi_novel.embedding, seed + 1)
+        fill_cnn_weights(inn.ll_novel.predictor, seed + 2)
+        fill_cnn_weights(inn.ll_novel.target, seed + 3)
+    inn.to(ptu.device)
+    inn.epi_novel.episodic_memory = torch.from_numpy(prefill_memory("randn", N, B, seed, CNN_CASE["mem_scale"]))
+    return inn
+
+
+def cnn_dropin_errors(mode):
+    """Runs the golden's 16 steps through the drop-in; returns the worst errors (used by the test and the probe tool)."""
+    import os
+    from ngu_b200.engine import DEFAULT_HYPR
+    from tests.conftest import ROOT
+    from tests.golden.make_golden import CNN_CASE, cnn_observations
+    g = np.load(os.path.join(ROOT, "tests", "golden_cnn", "dropin_cnn.npz"))
+    B, N, k, steps, seed = (int(v) for v in g["meta"])
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        inn = _cnn_dropin(DEFAULT_HYPR)
+        if mode == "graph":
+            inn.enable_cuda_graph()
+        obs = cnn_observations(B, steps, seed)
+        worst = dict(emb=0.0, d2=0.0, alpha=0.0, reward=0.0, r_epi=0.0, decided=0, slot_mismatch=0)
+        for t in range(steps):
+            o = torch.from_numpy(obs[t])
+            emb = inn.epi_novel._embed(o).cpu().numpy()
+            worst["emb"] = max(worst["emb"], float(np.abs(emb - g["emb"][t]).max()))
+            out = inn.compute_intrinsic_novelty(o)
+            assert out.shape == (B, 1) and out.device.type == "cpu"
+            got = out.numpy()[:, 0].astype(np.float64)
+            worst["reward"] = max(worst["reward"], float((np.abs(got - g["reward"][t]) / np.abs(g["reward"][t])).max()))
+            eng = inn.epi_novel._ensure_engine()
+            if mode == "eager":
+                alpha = eng._alpha_out.cpu().numpy().astype(np.float64)
+                worst["alpha"] = max(worst["alpha"], float(np.abs(alpha - g["alpha"][t]).max()))
+                r_epi = eng._r_epi.cpu().numpy().astype(np.float64)
+                want_epi = g["reward"][t] / np.clip(g["alpha"][t], 1.0, 5.0)
+                worst["r_epi"] = max(worst["r_epi"], float((np.abs(r_epi - want_epi) / np.abs(want_epi)).max()))
+            d2, idx = inn.epi_novel.knn()                                  # [B,k]
+            ref_d2, ref_idx = g["d2"][t], g["idx"][t]                      # [k+1,B]
+            worst["d2"] = max(worst["d2"], float((np.abs(d2.T - ref_d2[:k]) / ref_d2[:k]).max()))
+            gaps = (ref_d2[:-1] - ref_d2[1:]) / ref_d2[:-1]                # [k,B]
+            decided = (gaps > CNN_GAP).all(axis=0)
+            worst["decided"] += int(decided.sum())
+            worst["slot_mismatch"] += int((idx.T[:, decided] != ref_idx[:k][:, decided]).any(axis=0).sum())
+        mem = inn.epi_novel.episodic_memory.cpu().numpy()
+        worst["mem"] = float(np.abs(mem - g["mem_final"]).max())
+        worst["total"] = steps * B
+        inn.epi_novel._ensure_engine().close()
+        return worst
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+@pytest.mark.parametrize("mode", ["eager", "graph"])
+def test_real_cnn_dropin_matches_reference_golden(cuda_device, mode):
+    """compute_intrinsic_novelty(obs) with the REAL Embedding / RND CNNs (embedding.py:28-32,48-49,
+    lifelong_novelty.py:49-57, intrinsic_novelty.py:20-34), eager and as a CUDA-graph replay, against the reference's
+    recorded embeddings, modulators, rewards and k-NN lists."""
+    w = cnn_dropin_errors(mode)
+    assert w["emb"] <= CNN_EMB_ATOL, w
+    assert w["d2"] <= CNN_D2_RTOL, w
+    assert w["reward"] <= CNN_REWARD_RTOL, w
+    if mode == "eager":
+        assert w["alpha"] <= CNN_ALPHA_ATOL, w
+        assert w["r_epi"] <= CNN_REPI_RTOL, w
+    assert w["decided"] >= 0.9 * w["total"], w
+    assert w["slot_mismatch"] == 0, w
+    assert w["mem"] <= CNN_EMB_ATOL, w
