@@ -7,9 +7,12 @@ process per GPU.  The only coupling is the batch mean of the k-NN distances
 over ALL actors that feeds ``ed_rms`` (episodic_novelty.py:56 -> mpi_util.py:7-18):
 2k+1 doubles per step, exchanged between the scan and the finish kernel.  This
 is exactly what the reference's ``MPI.Allreduce`` does (mpi_util.py:17), here as
-one NCCL all-reduce over NVLink on the step's CUDA stream.  The log-only
-statistics (episodic_novelty.py:82, intrinsic_novelty.py:32) are a second tiny
-all-reduce after the finish kernel, off the critical path.
+an exchange over NVLink peer memory FUSED INTO THE EPILOGUE KERNEL (exchange="p2p":
+LL-tagged peer stores, csrc/p2p_exchange.cuh; the log-only sums of
+episodic_novelty.py:82 / intrinsic_novelty.py:32 ride on the next step's round), or,
+as the fallback transport (exchange="collective": gloo tests, no peer access), as
+one torch.distributed all-reduce between a split scan and finish plus a second tiny
+one for the log-only statistics.
 """
 from __future__ import annotations
 
@@ -72,10 +75,14 @@ class ShardedEpisodicEngine:
     def local_slice(self, x):
         return x[self.lo:self.hi]
 
-    def step(self, q_local: torch.Tensor, alpha_local: torch.Tensor | None = None):
-        """One hot-path step for this shard; returns device tensors (r_int, r_epi) of the local actors."""
+    def step(self, q_local: torch.Tensor, alpha_local: torch.Tensor | None = None, pipelined: bool = False, out=None):
+        """One hot-path step for this shard; returns device tensors (r_int, r_epi) of the local actors.
+        ``pipelined``: EpisodicEngine.step's software-pipelined launch (back-to-back steps with device-resident
+        inputs; with the p2p exchange the previous step's NVLink rendezvous then runs under this step's scan)."""
         eng = self.engine
         if self.world == 1 or self.exchange == "p2p":
+            if pipelined or out is not None:
+                return eng.step(q_local, alpha_local, pipelined=pipelined, out=out)
             return eng.step(q_local, alpha_local)      # p2p: the exchange happens inside the epilogue kernel
         eng.scan(q_local)
         self._sums.copy_(eng.rank_sums)

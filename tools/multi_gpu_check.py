@@ -58,12 +58,34 @@ def main():
         assert rel.max() <= 1e-5, f"rank {rank} step {t}: reward rel err {rel.max():.2e}"
         orc.reset(done)
         sh.reset(torch.from_numpy(done[sh.lo:sh.hi]))
+    n_steps = args.steps
+    if sh.exchange == "p2p":     # bursts of software-pipelined steps: the exchange of step t runs under the scan of step t+1
+        for steps in (2, 9, 30):
+            qh = rng.standard_normal((steps, B, 32), dtype=np.float32)
+            ah = (1.0 + 2.0 * rng.standard_normal((steps, B))).astype(np.float32)
+            qd, ad = torch.from_numpy(qh[:, sh.lo:sh.hi].copy()).cuda(), torch.from_numpy(ah[:, sh.lo:sh.hi].copy()).cuda()
+            r = torch.empty((steps, sh.hi - sh.lo), dtype=torch.float32, device="cuda")
+            e = torch.empty_like(r)
+            torch.cuda.synchronize()
+            for t in range(steps):
+                sh.step(qd[t], ad[t], pipelined=True, out=(r[t], e[t]))
+            torch.cuda.synchronize()
+            got = r.cpu().numpy()
+            for t in range(steps):
+                want = orc.step(qh[t], ah[t])
+                rel = np.abs(got[t] - want["reward"][sh.lo:sh.hi]) / np.abs(want["reward"][sh.lo:sh.hi])
+                worst = max(worst, float(rel.max()))
+                assert rel.max() <= 1e-5, f"rank {rank} pipelined burst of {steps}, step {t}: reward rel err {rel.max():.2e}"
+            d2, idx = sh.engine.topk()
+            assert np.array_equal(idx.T, want["idx"][:, sh.lo:sh.hi]), f"rank {rank}: kNN slots differ after a pipelined burst"
+            assert np.array_equal(d2.T.view(np.uint32), want["d2"][:, sh.lo:sh.hi].view(np.uint32))
+            n_steps += steps
     st = sh.get_state()          # collective in p2p mode: flushes the one-step-late log-only sums
     np.testing.assert_allclose(st["ed_mean"], orc.ed_rms.mean, rtol=1e-6)
     if sh.exchange != "collective" or sh.track_log_stats:
         # log-only trackers saw every actor of every step (global count), on every rank
-        assert abs(st["epi_count"] - (1e-4 + args.steps * B)) < 1e-6, st["epi_count"]
-        assert abs(st["intr_count"] - (1e-4 + args.steps * B)) < 1e-6
+        assert abs(st["epi_count"] - (1e-4 + n_steps * B)) < 1e-6, st["epi_count"]
+        assert abs(st["intr_count"] - (1e-4 + n_steps * B)) < 1e-6
     assert st["ed_count"] == float(orc.ed_rms.count)            # global actor count went into the tracker
     assert np.array_equal(sh.engine.dump_memory(), orc.memory[:, sh.lo:sh.hi])
     # every rank holds the same replicated statistics
