@@ -116,6 +116,8 @@ struct ngu_epi {
     double* log_sums = nullptr;      // [5]
     float* log_stash = nullptr;      // [2][B] rewards of the last fused step, not yet in the log-only trackers (log_absorb)
     int prefetch_tiles = 4;                  // experiments: NGU_EPI_PREFETCH_TILES
+    int arm_prefetch_tiles = 4;              // ... of a pre-armed host step, whose CTAs sit behind the doorbell for the whole host
+                                             // turnaround with HBM idle (NGU_EPI_ARM_PREFETCH_TILES)
     int l2_mode = 0; float l2_frac = 1.0f;   // L2 policy of the memory stream (ScanParams::l2_mode); NGU_EPI_L2=mode[,frac] overrides
     long long poll_limit_cycles = 4000000;   // ~2 ms without progress; NGU_EPI_DEBUG_POLL_LIMIT overrides (tests: 0)
     ScanSched sched{};
@@ -487,6 +489,8 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
         if (got >= 2 && f > 0.0f && f <= 1.0f) h->l2_frac = f;
     }
     if (const char* e = getenv("NGU_EPI_PREFETCH_TILES")) h->prefetch_tiles = atoi(e) < 0 ? 0 : (atoi(e) > kMaxPrefetchTiles ? kMaxPrefetchTiles : atoi(e));
+    h->arm_prefetch_tiles = h->prefetch_tiles;
+    if (const char* e = getenv("NGU_EPI_ARM_PREFETCH_TILES")) h->arm_prefetch_tiles = atoi(e) < 0 ? 0 : (atoi(e) > kMaxPrefetchTiles ? kMaxPrefetchTiles : atoi(e));
     CREATE_TRY(cudaMalloc(&h->state, sizeof(DevState)));
     CREATE_TRY(cudaMemset(h->state, 0, sizeof(DevState)));
     {
@@ -627,7 +631,8 @@ static int launch_scan(ngu_epi* h, const float* q_dev, cudaStream_t s, const Cha
     sp.largest = h->consts.largest; sp.sqrt_dist = h->consts.sqrt_dist; sp.neg_zero2 = kNegZero2;
     sp.tiles_per_actor = h->tiles_per_actor;
     sp.max_cand = h->max_cand; sp.sched = h->sched; sp.sched_ctr = cx.sched_ctr;
-    sp.leftover = cx.leftover; sp.poll_limit_cycles = h->poll_limit_cycles; sp.prefetch_tiles = h->prefetch_tiles;
+    sp.leftover = cx.leftover; sp.poll_limit_cycles = h->poll_limit_cycles;
+    sp.prefetch_tiles = h->arm_seq_next != 0u ? h->arm_prefetch_tiles : h->prefetch_tiles;
     sp.l2_mode = h->l2_mode; sp.l2_frac = h->l2_frac;
     sp.actor_state = cx.actor_state;
     sp.timeouts = reinterpret_cast<unsigned long long*>(&h->state->exchange_timeouts);

@@ -219,7 +219,7 @@ __device__ __forceinline__ u64 ld_volatile_u64(const u64* src) {
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
     return v;
 }
-constexpr int kMaxPrefetchTiles = 16;
+constexpr int kMaxPrefetchTiles = 64;
 constexpr int kLLSpinLimit = 1 << 22;   // ~ seconds; a healthy wait is about one tile time
 // floor word -> the largest key that is certainly NOT needed (0 = no floor)
 __device__ __forceinline__ u64 floor_key(u64 floor_word, uint32_t tag) {

@@ -66,6 +66,10 @@ def main():
         dev = torch.device("cpu")
         dist.init_process_group("gloo")
     sync = torch.cuda.synchronize if cuda else (lambda: None)
+    # the check compares a sliced batch with the full batch to 2e-4: keep the convolutions / GEMMs in full float32
+    # (TF32's 10-bit mantissa alone moves a gradient by ~1e-3); the timing section below switches it back on
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     from ngu_b200.learner_allreduce import GradAllReducer, attach_r2d2_allreduce
 
     T, Bg = 8, 8 * world                               # global batch, sliced over the ranks
@@ -128,6 +132,7 @@ def main():
         assert same and red.copies_in == 0
         red.close()
 
+    torch.backends.cudnn.allow_tf32 = True
     # ---- timing: does the all-reduce hide behind backward? ----
     def timed(mode, iters=20 if cuda else 1):
         learner, hy = build_learner()
