@@ -116,6 +116,8 @@ struct ngu_epi {
     double* log_sums = nullptr;      // [5]
     float* log_stash = nullptr;      // [2][B] rewards of the last fused step, not yet in the log-only trackers (log_absorb)
     int prefetch_tiles = 4;                  // experiments: NGU_EPI_PREFETCH_TILES
+    int cta_merge = 0;                       // static schedules: two-level merge (scan_topk.cuh: static_cta_finish); set by
+                                             // plan_geometry when an actor is cut into many runs, NGU_EPI_CTA_MERGE=0|1 forces it
     int arm_prefetch_tiles = 4;              // ... of a pre-armed host step, whose CTAs sit behind the doorbell for the whole host
                                              // turnaround with HBM idle (NGU_EPI_ARM_PREFETCH_TILES)
     int l2_mode = 0; float l2_frac = 1.0f;   // L2 policy of the memory stream (ScanParams::l2_mode); NGU_EPI_L2=mode[,frac] overrides
@@ -333,6 +335,10 @@ void plan_geometry(ngu_epi* h) {
         min_chunk = static_cast<int>(sc.n1 > 0 && sc.s1 < narrow ? sc.s1 : narrow);
         sc.n_chunks = sc.n1 + sc.rows * sc.cols;
     }
+    // static schedules: with many runs per actor the CTA-level combine pays (measured: >= 117 runs win 2-5 us after the
+    // last tile, 32-72 runs lose 3-6 us)
+    h->cta_merge = sc.n_chunks == sc.n1 && h->tiles_per_actor / sc.s1 >= 96 ? 1 : 0;
+    if (const char* e = getenv("NGU_EPI_CTA_MERGE")) h->cta_merge = (atoi(e) != 0 && sc.n_chunks == sc.n1) ? 1 : 0;
     // worst case every run publishes k candidates; runs per actor <= chunks overlapping it
     h->max_cand = ((h->tiles_per_actor + min_chunk - 1) / min_chunk + 3) * h->cfg.k;
 }
@@ -633,6 +639,7 @@ static int launch_scan(ngu_epi* h, const float* q_dev, cudaStream_t s, const Cha
     sp.max_cand = h->max_cand; sp.sched = h->sched; sp.sched_ctr = cx.sched_ctr;
     sp.leftover = cx.leftover; sp.poll_limit_cycles = h->poll_limit_cycles;
     sp.prefetch_tiles = h->arm_seq_next != 0u ? h->arm_prefetch_tiles : h->prefetch_tiles;
+    sp.cta_merge = h->cta_merge;
     sp.l2_mode = h->l2_mode; sp.l2_frac = h->l2_frac;
     sp.actor_state = cx.actor_state;
     sp.timeouts = reinterpret_cast<unsigned long long*>(&h->state->exchange_timeouts);

@@ -117,6 +117,7 @@ struct ScanParams {
                                    // merge jobs (all zero between launches), [2] launch epoch = tag of this launch's
                                    // candidates and floors (never 0)
     int32_t prefetch_tiles;        // tiles per warp prefetched into L2 before the grid dependency resolves
+    int32_t cta_merge;             // static schedules: 1 = two-level merge (CTA combine in shared memory first), see static_cta_finish
     int32_t l2_mode;               // L2 eviction policy of the memory stream: 0 evict_first (read once per step, much larger
     float l2_frac;                 // than L2), 1 evict_normal, 2 evict_last for a fraction l2_frac of the lines (by address
                                    // hash: the same lines every step), rest evict_first.  Experiment knob (NGU_EPI_L2):
@@ -567,6 +568,130 @@ __device__ __forceinline__ void finish_static(const ScanParams& p, int actor, in
     if (tl && lane == 0) { tl[5] = dbg_t0; tl[6] = static_cast<unsigned long long>(nparts * k); tl[7] = globaltimer_ns(); }
 }
 
+// TWO-LEVEL merge for static schedules whose actors are cut into MANY runs (ScanParams::cta_merge; chosen by the host
+// when an actor has >= 96 runs: 1 x 30 000 has 235).  With few runs the single-level protocol above is shorter - the
+// CTA-level combine is a serial phase of ~2 us in front of the same round trips (measured: 64 x 5 000, 32 runs per
+// actor, 4.7 -> 10.7 us after the last tile; 1 x 30 000 9-11 -> 5.5 us).
+// These are bound by latency, not
+// bandwidth, so the merge is the shortest chain we know, in two levels:
+//   1. inside the CTA, through shared memory.  The eight chunks of a CTA are consecutive in tile space, so its warps'
+//      partial runs (a chunk's first and last run; the runs in between cover whole actors and are final) fall into a
+//      few groups of one actor each.  Every warp leaves its <= 2 partial lists in shared memory and arrives on a CTA
+//      counter; the LAST warp to arrive combines each group - the lists are sorted, so they are offered rank-major,
+//      32 / L ranks of the L lists per batch: one bitonic batch merge and a few inserts, ~1 us;
+//   2. between the CTAs of an actor, through global memory as before: the CTA publishes ONE list per actor at the
+//      slot that follows from its block index (k epoch-tagged entries, no reservation round trip), counts its tiles
+//      on the actor's counter, and the CTA whose arrival completes the actor merges the <= tiles_per_actor /
+//      (WARPS * s1) + 2 lists - exact knowledge, no polling for arrivals, only for the entries' tags.
+// 1 x 30 000: 235 per-warp lists merged by one warp (8-11 us after the last tile) became 30 CTA lists.
+// A group that covers its whole actor inside one CTA is written directly.  All atomics of a CTA's groups are issued
+// before any of their results is looked at (lane g keeps the result of group g).
+template <int WARPS>
+__device__ __forceinline__ void static_cta_finish(const ScanParams& p, uint32_t cta_area, int warp, int lane, uint32_t tag,
+                                                  int n_active, int e0_actor, int e0_tiles, u64 e0_key, int e1_actor,
+                                                  int e1_tiles, u64 e1_key, uint32_t stage, unsigned long long* tl) {
+    const int k = p.k, tpa = p.tiles_per_actor;
+    const uint32_t lists = cta_area;                           // [WARPS][2][32] u64
+    const uint32_t meta = cta_area + WARPS * 2 * 32 * 8;       // [WARPS][2] {actor, tiles}
+    const uint32_t ctr = meta + WARPS * 2 * 8;                 // arrivals (zeroed at kernel start)
+    // ---- level 1: leave this warp's partial lists in shared memory, arrive ----
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(lists + ((warp * 2 + 0) * 32 + lane) * 8), "l"(lane < k ? e0_key : 0ull) : "memory");
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(lists + ((warp * 2 + 1) * 32 + lane) * 8), "l"(lane < k ? e1_key : 0ull) : "memory");
+    if (lane == 0) {
+        asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(meta + (warp * 2 + 0) * 8), "r"(e0_actor), "r"(e0_tiles) : "memory");
+        asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(meta + (warp * 2 + 1) * 8), "r"(e1_actor), "r"(e1_tiles) : "memory");
+    }
+    __syncwarp();
+    unsigned arrived = 0;
+    if (lane == 0) {
+        __threadfence_block();
+        asm volatile("atom.shared.acq_rel.cta.add.u32 %0, [%1], 1;" : "=r"(arrived) : "r"(ctr) : "memory");
+    }
+    arrived = __shfl_sync(kFull, arrived, 0);
+    if (static_cast<int>(arrived) != n_active - 1) {           // not the last warp of the CTA
+        if (tl && lane == 0) tl[5] = 0ull;
+        return;
+    }
+    __threadfence_block();
+    // ---- the CTA's combiner: groups of consecutive entries with the same actor ----
+    const int E = 2 * n_active;                                // <= 32 entries, one per lane
+    int my_actor = -1, my_tiles = 0;
+    if (lane < E) asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(my_actor), "=r"(my_tiles) : "r"(meta + lane * 8) : "memory");
+    const int cs = WARPS * p.sched.s1;                         // tiles per CTA
+    int g_actor = -1, g_tiles = 0;                             // lane g: group g (actor, tiles; tiles = 0: written directly)
+    u64 g_ret = 0ull;                                          // lane g: UNREAD result of group g's arrive atomic
+    int n_groups = 0;
+    unsigned todo = __ballot_sync(kFull, my_actor >= 0);
+    const unsigned long long dbg_t0 = tl ? globaltimer_ns() : 0ull;
+#pragma unroll 1
+    while (todo) {
+        const int first = __ffs(todo) - 1;
+        const int actor = __shfl_sync(kFull, my_actor, first);
+        const bool mine = my_actor == actor;                   // entries of one actor are consecutive, but need not be
+        const unsigned members = __ballot_sync(kFull, mine);   // (an absent first run leaves a hole): use the mask
+        todo &= ~members;
+        int tiles = mine ? my_tiles : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tiles += __shfl_xor_sync(kFull, tiles, o);
+        const int L = __popc(members);
+        // lane -> (list, rank): list = the (lane % L)-th member, ranks [b * R, (b + 1) * R) in batch b
+        const int R = 32 / L;
+        int nth = lane % L, entry = 0;
+        {
+            unsigned mm = members;
+            for (int i = 0; i < nth; ++i) mm &= mm - 1;
+            entry = __ffs(mm) - 1;
+        }
+        WarpTopK m;
+        m.reset();
+#pragma unroll 1
+        for (int r0 = 0; r0 < k; r0 += R) {
+            const int r = r0 + lane / L;
+            u64 key = 0ull;
+            if (lane / L < R && r < k) asm volatile("ld.shared.u64 %0, [%1];" : "=l"(key) : "r"(lists + (entry * 32 + r) * 8) : "memory");
+            const unsigned passed = __ballot_sync(kFull, key > m.thr);
+            if (!passed) break;                                // sorted lists: no deeper rank can pass either
+            m.insert(key, passed, lane, k);
+        }
+        if (tiles == tpa) {                                    // the CTA covered the whole actor
+            write_knn(knn_out(p, actor), k, knn_flags(p), m.lkey, lane);
+        } else {
+            const int t0 = actor * tpa;
+            const int slot = static_cast<int>(blockIdx.x) - t0 / cs;
+            u64* cand = p.cand + static_cast<int64_t>(actor) * p.max_cand * 2;
+            if (slot < 0 || (slot + 1) * k > p.max_cand) {     // cannot happen; never write out of bounds
+                if (lane == 0) atomicAdd(p.timeouts, 1ull);
+            } else {
+                if (lane < k) st_ll(cand + (slot * k + lane) * 2, m.lkey, tag);
+                if (lane == n_groups) {
+                    g_actor = actor; g_tiles = tiles;
+                    g_ret = atomicAdd(actor_ctr(p, actor), static_cast<u64>(tiles) << 32);
+                }
+                ++n_groups;
+            }
+        }
+    }
+    // ---- level 2: the groups whose arrival completed their actor ----
+    if (tl && lane == 0) { tl[5] = dbg_t0; tl[6] = globaltimer_ns(); tl[7] = tl[6]; }   // combiner: start, level 1 done, level 2 done
+#pragma unroll 1
+    for (int g = 0; g < n_groups; ++g) {
+        const int actor = __shfl_sync(kFull, g_actor, g);
+        const int tiles = __shfl_sync(kFull, g_tiles, g);
+        const u64 prev = __shfl_sync(kFull, g_ret, g);
+        if (static_cast<uint32_t>(prev >> 32) + static_cast<uint32_t>(tiles) != static_cast<uint32_t>(tpa)) continue;
+        if (lane == 0) *actor_ctr(p, actor) = 0ull;            // re-arm for the next launch
+        if (p.debug & 8) continue;
+        const int t0 = actor * tpa;
+        const int nparts = (t0 + tpa - 1) / cs - t0 / cs + 1;  // CTAs that overlap the actor
+        const u64* cand = p.cand + static_cast<int64_t>(actor) * p.max_cand * 2;
+        WarpTopK m;
+        m.reset();
+        consume_lists(p, cand, nparts, tag, lane, stage, m);
+        write_knn(knn_out(p, actor), k, knn_flags(p), m.lkey, lane);
+        if (tl && lane == 0) tl[7] = globaltimer_ns();
+    }
+}
+
 // ---- PTX wrappers ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -696,7 +821,8 @@ struct ScanCfg {
     static constexpr int kAuxBytes = 128 + 16 + 128;   // per stage: query row + {floor, ctr} of the actor whose run starts there
                                                        // + the row the previous step is appending (pipelined launches)
     // tiles + 1024 B alignment slack + barriers + per-stage descriptors + per-stage run-start data
-    static constexpr int kSmemBytes = WARPS * STAGES * kTileBytes + 1024 + WARPS * STAGES * (16 + kAuxBytes);
+    static constexpr int kCtaMergeBytes = WARPS * (2 * 32 * 8 + 2 * 8) + 16;   // static schedules: the CTA-level combine
+    static constexpr int kSmemBytes = WARPS * STAGES * kTileBytes + 1024 + WARPS * STAGES * (16 + kAuxBytes) + kCtaMergeBytes;
     // CTAs per SM the shared memory allows (227 KB per SM): tells ptxas how many registers it may use.
     // Without it ptxas squeezes the kernel into 80 registers and spills producer state in the hot loop.
     static constexpr int kMaxCtasPerSm = (227 * 1024) / (kSmemBytes + 1024) > 0 ? (227 * 1024) / (kSmemBytes + 1024) : 1;
@@ -721,11 +847,15 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
     const uint32_t aux0 = desc0 + WARPS * STAGES * 8;     // 16-byte aligned: everything before it is a multiple of 16
     const uint32_t my_aux = aux0 + warp * STAGES * Cfg::kAuxBytes;
 
+    const uint32_t cta_area = aux0 + WARPS * STAGES * Cfg::kAuxBytes;   // static schedules: lists, meta, arrival counter
+
     const int gw = blockIdx.x * WARPS + warp;
     const int n_warps = gridDim.x * WARPS;
     const unsigned long long tl0 = p.timeline ? globaltimer_ns() : 0ull;
     unsigned long long tl1 = 0ull;
     const ScanSched& sc = p.sched;
+    if (threadIdx.x == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(cta_area + WARPS * (2 * 32 * 8 + 2 * 8)), "r"(0u) : "memory");
+    __syncthreads();                // the only CTA-wide barrier: the arrival counter of static_cta_finish is zero
     if (gw >= sc.n_chunks) return;  // whole warp exits together; no CTA-wide barriers below
 
     const int tpa = p.tiles_per_actor;
@@ -890,7 +1020,16 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
         if (b < 0) break;
         if (b != cur) {
             if (cur >= 0 && !(p.debug & 4)) {
-                if (static_sched) {
+                if (static_sched && p.cta_merge) {
+                    if (run_tiles == tpa) {            // this warp scanned the whole actor: final
+                        write_knn(knn_out(p, cur), k, knn_flags(p), top.lkey, lane);
+                    } else {                           // the chunk's first run: kept in registers until the warp has streamed
+                        if (pend_actor >= 0 && lane == 0) atomicAdd(p.timeouts, 1ull);   // (cannot happen: only a chunk's
+                        pend_actor = cur;                                                 // first and last run are partial)
+                        pend_n = run_tiles;
+                        pend_key = top.lkey;
+                    }
+                } else if (static_sched) {
                     if (pend_actor >= 0)   // (cannot happen: only a chunk's first and last run are partial)
                         finish_static(p, pend_actor, pend_n, pend_ret, tag, lane, my_tiles, nullptr);
                     pend_actor = flush_run_static(p, cur, run_tiles, run_first, tag, top, lane, pend_ret) ? cur : -1;
@@ -959,11 +1098,18 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
     const unsigned long long tl2 = p.timeline ? globaltimer_ns() : 0ull;
     const int workers = n_warps < sc.n_chunks ? n_warps : sc.n_chunks;
     unsigned long long* tl_rec = p.timeline ? p.timeline + static_cast<int64_t>(gw) * 8 : nullptr;
-    if (cur >= 0 && !(p.debug & 4) && static_sched) {
+    if (cur >= 0 && !(p.debug & 4) && static_sched && !p.cta_merge) {
         u64 ret = 0ull;
         const bool last_partial = flush_run_static(p, cur, run_tiles, run_first, tag, top, lane, ret);
         if (pend_actor >= 0) finish_static(p, pend_actor, pend_n, pend_ret, tag, lane, my_tiles, tl_rec);
         if (last_partial) finish_static(p, cur, run_tiles, ret, tag, lane, my_tiles, tl_rec);
+    } else if (cur >= 0 && !(p.debug & 4) && static_sched) {
+        int last_actor = -1;
+        if (run_tiles == tpa) write_knn(knn_out(p, cur), k, knn_flags(p), top.lkey, lane);
+        else last_actor = cur;
+        const int rest = sc.n_chunks - static_cast<int>(blockIdx.x) * WARPS;
+        static_cta_finish<WARPS>(p, cta_area, warp, lane, tag, rest < WARPS ? rest : WARPS, pend_actor, pend_n, pend_key,
+                                 last_actor, run_tiles, top.lkey, my_tiles, tl_rec);
     } else if (cur >= 0 && !(p.debug & 4)) {
         if (pend_actor >= 0) complete_pending(p, pend_actor, pend_key, pend_n, pend_ret, tag, lane);
         if (flush_run(p, cur, run_tiles, tag, top, lane, pend_key, pend_n, pend_ret))

@@ -276,3 +276,55 @@ def test_host_step_input_staging(cuda_device, monkeypatch, stage, B):
         assert _rel(r_int.astype(np.float64), ref["reward"]).max() <= REL_TOL
     assert np.array_equal(eng.dump_memory(), orc.memory)
     eng.close()
+
+
+@pytest.mark.parametrize("B,N,k,mode", [(16, 3000, 10, "reference"), (5, 2049, 32, "reference"), (64, 5000, 10, "reference"),
+                                         (1, 30000, 10, "reference"), (1024, 100, 10, "reference"), (3, 64, 10, "reference"),
+                                         (9, 4097, 10, "paper"), (2, 33, 10, "reference"), (40, 96, 4, "reference")])
+@pytest.mark.parametrize("cta_merge", ["0", "1"])
+def test_static_merge_levels_vs_oracle(cuda_device, monkeypatch, B, N, k, mode, cta_merge):
+    """Static schedules merge an actor's runs in one level (every warp publishes its list, the last arrival merges
+    them) or in two (CTA combine in shared memory first, scan_topk.cuh::static_cta_finish); the library picks by the
+    number of runs per actor.  Both forced here on shapes where a CTA holds part of an actor, exactly one actor,
+    several whole actors and the boundaries between them; ordinary steps and a burst of pipelined ones."""
+    import torch
+    from ngu_b200.engine import EpisodicEngine
+    from oracle.episodic_oracle import EpisodicOracle
+    monkeypatch.setenv("NGU_EPI_CTA_MERGE", cta_merge)
+    rng = np.random.default_rng(B * 31 + N + k)
+    mem0 = rng.standard_normal((N, B, 32), dtype=np.float32)
+    mem0[rng.random(N) < 0.2] = 0.0
+    orc = EpisodicOracle(B, N, k=k, mode=mode, use_c_scan=B * N > 50000)
+    orc.memory[...] = mem0
+    eng = EpisodicEngine(B, N, k=k, mode=mode, device=0)
+    assert eng.scan_geometry()["dynamic_chunk_tiles"] == 0
+    eng.load_memory(mem0)
+    for t in range(5):
+        q = rng.standard_normal((B, 32), dtype=np.float32)
+        alpha = (1.0 + 2.0 * rng.standard_normal(B)).astype(np.float32)
+        ref = orc.step(q, alpha)
+        r_int, _ = eng.step_host(q, alpha)
+        d2, idx = eng.topk()
+        assert np.array_equal(idx.T, ref["idx"]), f"step {t}: kNN slots differ"
+        assert np.array_equal(d2.T.view(np.uint32), ref["d2"].view(np.uint32)), f"step {t}: d^2 bits differ"
+        assert _rel(r_int.astype(np.float64), ref["reward"]).max() <= REL_TOL
+        done = rng.random(B) < 0.3
+        orc.reset(done)
+        eng.reset_host(done)
+    T = 12
+    qs = rng.standard_normal((T, B, 32), dtype=np.float32)
+    al = (1.0 + 2.0 * rng.standard_normal((T, B))).astype(np.float32)
+    qd, ad = torch.from_numpy(qs).cuda(), torch.from_numpy(al).cuda()
+    r = torch.empty((T, B), dtype=torch.float32, device="cuda")
+    e = torch.empty_like(r)
+    for t in range(T):
+        eng.step(qd[t], ad[t], pipelined=True, out=(r[t], e[t]))
+    got = r.cpu().numpy()
+    for t in range(T):
+        ref = orc.step(qs[t], al[t])
+        assert _rel(got[t].astype(np.float64), ref["reward"]).max() <= REL_TOL, f"pipelined step {t}"
+    d2, idx = eng.topk()
+    assert np.array_equal(idx.T, ref["idx"]) and np.array_equal(d2.T.view(np.uint32), ref["d2"].view(np.uint32))
+    assert np.array_equal(eng.dump_memory(), orc.memory)
+    assert eng.get_state()["exchange_timeouts"] == 0
+    eng.close()

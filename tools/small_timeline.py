@@ -32,9 +32,13 @@ for B, N in SHAPES:
         s = st.astype(np.int64)
         acc.append([ (t[:, 0].max() - t0), (t[:, 1].min() - t0), (t[:, 1].max() - t0), (t[:, 2].min() - t0), (t[:, 2].max() - t0),
                      (t[:, 3].max() - t0), (s[8] - t0), (s[0] - t0), (s[7] - t0)])
+    c = t[t[:, 5] > 0]                                  # static schedules: the CTA combiners of the last step
+    comb = dict(combiners=int(len(c)), start_after_own_stream_end=pct((c[:, 5] - c[:, 2]) / 1e3), level1_us=pct((c[:, 6] - c[:, 5]) / 1e3),
+                level2_us=pct((c[:, 7] - c[:, 6]) / 1e3), exit_after_level2=pct((c[:, 3] - c[:, 7]) / 1e3),
+                last_combiner_start=round(float((c[:, 5].max() - t0) / 1e3), 2)) if len(c) else {}
     m = np.mean(np.array(acc), axis=0) / 1e3
     names = ["last_warp_start", "first_tile_min", "first_tile_max", "stream_end_min", "stream_end_max", "flush_merge_end_max",
              "epilogue_entry", "epilogue_wait_return", "epilogue_last_stamp"]
     print(json.dumps(dict(B=B, N=N, warps=int(len(t)), step_us=round(step_us, 2), geometry=eng.scan_geometry(),
-                          **{n: round(float(v), 2) for n, v in zip(names, m)})), flush=True)
+                          **{n: round(float(v), 2) for n, v in zip(names, m)}, **comb)), flush=True)
     eng.close()
