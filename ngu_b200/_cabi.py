@@ -76,6 +76,30 @@ SYMBOLS = {
     "ngu_epi_scan_timing_end": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
 }
 
+
+
+class NguSeqCfg(C.Structure):        # struct ngu_seq_cfg, include/ngu_seq.h
+    _fields_ = [("n_actors", C.c_int32), ("seq_len", C.c_int32), ("n_step", C.c_int32), ("overlap", C.c_int32),
+                ("obs_elems", C.c_int32), ("store_capacity", C.c_int32), ("device", C.c_int32), ("reserved0", C.c_int32)]
+
+
+class NguSeqViews(C.Structure):      # struct ngu_seq_views: device pointers
+    _fields_ = [(n, _P) for n in ("state", "prev_action", "curr_action", "intrinsic_reward", "extrinsic_reward",
+                                  "local_mem_idx", "st_state", "st_prev_action", "st_curr_action", "st_intrinsic_reward",
+                                  "st_extrinsic_reward", "st_augmented_reward", "st_nstep_reward", "st_actor", "counters",
+                                  "last_pushed")]
+
+
+# exactly the symbols include/ngu_seq.h declares
+SEQ_SYMBOLS = {
+    "ngu_seq_create": (C.c_int, [C.POINTER(NguSeqCfg), C.POINTER(_P)]),
+    "ngu_seq_destroy": (None, [_P]),
+    "ngu_seq_last_error": (C.c_char_p, [_P]),
+    "ngu_seq_views_get": (C.c_int, [_P, C.POINTER(NguSeqViews)]),
+    "ngu_seq_set_factors": (C.c_int, [_P, _P, _P]),
+    "ngu_seq_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+}
+
 _lib = None
 
 
@@ -93,7 +117,7 @@ def load() -> C.CDLL:
             f"{LIB_PATH} is missing. Build it with `python -m ngu_b200.build` "
             "(or __graft_entry__.build()). ngu_b200 has no CPU / PyTorch fallback.")
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in SYMBOLS.items():
+    for name, (res, args) in list(SYMBOLS.items()) + list(SEQ_SYMBOLS.items()):
         fn = getattr(lib, name)          # AttributeError if the ABI is out of date
         fn.restype = res
         fn.argtypes = args

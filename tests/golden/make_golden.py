@@ -273,6 +273,98 @@ def run_rnd_case(torch, model_hypr):
     print("rnd_tail: alpha[0,:3] =", out["alpha_6"][0, :3])
 
 
+# ---- collect_sequence / push_collected buffering --------------------------------------------------------
+def run_collect_case(torch, model_hypr):
+    """Golden for the buffering half of NGUAgent.collect_sequence + push_collected (ngu_agent.py:56-94, :96-155): the
+    UNMODIFIED reference methods executed on a stand-in `self` that carries exactly the attributes NGUAgent.__init__
+    creates (:22-49; a small observation shape keeps the fixture small) and stub collaborators: an environment that
+    returns seeded synthetic observations / rewards / episode ends, an intrinsic-novelty module that returns seeded
+    rewards, TD errors of zero (the R2D2 networks are outside this path) and a replay memory that records what
+    `push` receives.  n_actors = 1: the case in which the reference's advanced indexing is the per-actor write
+    (include/ngu_seq.h).  R2D2Actor.compute_nstep_reward and NGUAgent.compute_priorities are the reference's own."""
+    import types
+    from ngu.models.ngu.ngu_agent import NGUAgent
+    from ngu.models.r2d2.r2d2_actor import R2D2Actor
+    B, obs_shape, calls, seed = 1, (1, 6, 6), 3, 41
+    hy = dict(model_hypr)
+    rng = np.random.default_rng(seed)
+    rec = dict(obs=[], act=[], intr=[], extr=[], done=[])
+
+    class Env:
+        def reset(self):
+            return torch.zeros((B,) + obs_shape)
+
+        def step(self, action):
+            o = torch.from_numpy(rng.standard_normal((B,) + obs_shape, dtype=np.float32))
+            r = torch.from_numpy(rng.standard_normal((B, 1), dtype=np.float32))
+            d = rng.random(B) < 0.01
+            rec["act"].append(action.numpy().copy()); rec["obs"].append(o.numpy().copy())
+            rec["extr"].append(r.numpy().copy()); rec["done"].append(d.copy())
+            return o, r, d, None
+
+    class Intr:
+        def compute_intrinsic_novelty(self, obs):
+            r = torch.from_numpy(np.abs(rng.standard_normal((B, 1), dtype=np.float32)))
+            rec["intr"].append(r.numpy().copy())
+            return r
+
+        def reset_memory_if_done(self, done):
+            pass
+
+    class Memory:
+        def __init__(self):
+            self.pushed = []
+
+        def push(self, *a):
+            self.pushed.append([x.clone() if torch.is_tensor(x) else x for x in a])
+
+    actor = types.SimpleNamespace(model_hypr=hy, explr_beta=torch.full((B, 1), 0.3), explr_beta_onehot=torch.zeros((B, 32)),
+                                  discounts=torch.full((B, 1), 0.997), reset_hiddenstate_if_done=lambda d: None,
+                                  policy=types.SimpleNamespace(get_hidden_state=lambda to_cpu=False: (None, None),
+                                                               set_hidden_state=lambda h, c: None))
+    actor.compute_nstep_reward = types.MethodType(R2D2Actor.compute_nstep_reward, actor)
+    me = types.SimpleNamespace()
+    me.envs, me.n_actors, me.n_act, me.obs_shape, me.model_hypr = Env(), B, 18, obs_shape, hy
+    me.burnin_period = hy["burnin_period"]                                         # ngu_agent.py:22-27
+    me.seq_len = hy["trace_length"] + me.burnin_period
+    me.n_step = hy["n_step"]
+    me.memory, me.r2d2_actor, me.intrinsic_novelty = Memory(), actor, Intr()
+    me.init_hx, me.init_cx = torch.zeros((B, 4)), torch.zeros((B, 4))
+    me.local_mem_idx = torch.zeros((B,), dtype=torch.int64)                        # :36-49
+    me.mem_seq_len = me.seq_len + me.n_step
+    me.mem_collected_mask = torch.full((B,), me.mem_seq_len - 1)
+    me.state = torch.zeros((B, me.mem_seq_len) + obs_shape, dtype=torch.float32)
+    me.prev_action = torch.zeros((B, me.mem_seq_len, 1), dtype=torch.int64)
+    me.curr_action = torch.zeros((B, me.mem_seq_len, 1), dtype=torch.int64)
+    me.intrinsic_reward = torch.zeros((B, me.mem_seq_len, 1), dtype=torch.float32)
+    me.extrinsic_reward = torch.zeros((B, me.mem_seq_len, 1), dtype=torch.float32)
+    me.prev_obs = me.envs.reset()
+    me.prev_act = torch.zeros((B, 1), dtype=torch.int64)
+    me.prev_ext_rew, me.prev_int_rew = torch.zeros((B, 1)), torch.zeros((B, 1))
+    me.compute_td_error = lambda n, *a, **k: torch.zeros((me.seq_len - me.burnin_period, int(n), 1))
+    for name in ("push_collected", "compute_priorities", "_reset_prev_if_done", "_reset_local_mem_if_done"):
+        setattr(me, name, types.MethodType(getattr(NGUAgent, name), me))
+    torch.manual_seed(seed)
+    for _ in range(calls):
+        NGUAgent.collect_sequence(me, random_policy=True)                          # THE reference call: 300 env steps each
+    names = ("state", "prev_action", "curr_action", "intrinsic_reward", "extrinsic_reward", "augmented_reward", "nstep_reward")
+    out = {"in_" + k: np.stack(v) for k, v in rec.items()}
+    for j, nm in enumerate(names):
+        out["push_" + nm] = np.stack([p[j].numpy()[0] for p in me.memory.pushed])
+    out["final_idx"] = me.local_mem_idx.numpy().copy()
+    for nm in names[:5]:
+        out["final_" + nm] = getattr(me, nm).numpy().copy()
+    out["beta"] = actor.explr_beta.numpy().copy()
+    out["disc_pow"] = torch.cat([actor.discounts ** i for i in range(me.n_step)], dim=1).numpy().copy()
+    out["meta"] = np.array([B, me.seq_len, me.n_step, hy["overlapping_period"], calls * 300], dtype=np.int64)
+    out["obs_shape"] = np.array(obs_shape, dtype=np.int64)
+    out["versions"] = np.array([f"torch {torch.__version__}", f"numpy {np.__version__}"])
+    os.makedirs(os.path.join(HERE, "..", "golden_seq"), exist_ok=True)
+    np.savez_compressed(os.path.join(HERE, "..", "golden_seq", "collect_b1.npz"), **out)
+    print(f"collect_b1: {calls * 300} steps, {len(me.memory.pushed)} sequences pushed, episode ends {int(out['in_done'].sum())}, "
+          f"final idx {out['final_idx']}")
+
+
 def lane8_probe(torch):
     """torch CPU's D=32 sum order must be the lane-8 order
     on the machine that produced the goldens."""
@@ -301,6 +393,8 @@ def main():
         run_rnd_case(torch, model_hypr)
     if not only or "dropin_cnn" in only:
         run_cnn_case(torch, IntrinsicNovelty, model_hypr)
+    if not only or "collect_b1" in only:
+        run_collect_case(torch, model_hypr)
 
 
 if __name__ == "__main__":
