@@ -441,8 +441,10 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
                 const double mean = s_scal[SC_LL], var = s_scal[SC_LL + 1], count = s_scal[SC_LL + 2];
                 const double delta = static_cast<double>(bmean) - mean;
                 const double totc = count + n_b;
-                const double new_mean = mean + f64_div(delta * n_b, totc);
-                const double m2 = var * count + m_b + f64_div(delta * delta * count * n_b, totc);
+                // every product and sum rounded separately, like numpy (no FMA contraction): mpi_util.py:59-73
+                const double new_mean = __dadd_rn(mean, f64_div(__dmul_rn(delta, n_b), totc));
+                const double m2 = __dadd_rn(__dadd_rn(__dmul_rn(var, count), m_b),
+                                            f64_div(__dmul_rn(__dmul_rn(__dmul_rn(delta, delta), count), n_b), totc));
                 const double new_var = f64_div(m2, totc);
                 st->ll_mean = new_mean; st->ll_var = new_var; st->ll_count = totc;
                 s_ll[0] = new_mean;
@@ -550,7 +552,7 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
             const double delta = bm - s_mean[j];
             const double totc = count + n_b;
             if (threadIdx.x < 32) {
-                const double new_mean = s_mean[j] + f64_div(delta * n_b, totc);
+                const double new_mean = __dadd_rn(s_mean[j], f64_div(__dmul_rn(delta, n_b), totc));   // no FMA contraction (numpy)
                 st->ed_mean[j] = new_mean;
                 mean32[j] = static_cast<float>(new_mean);   // ptu.to_tensor(...).float(), pytorch_util.py:20
             } else {
@@ -561,7 +563,8 @@ __global__ void __launch_bounds__(THREADS) epilogue_kernel(const EpilogueParams 
                 const float b_std = f32_sqrt(msd);
                 const float b_var = __fmul_rn(b_std, b_std);                      // np.square(batch_std), :56
                 const double m_b = static_cast<double>(__fmul_rn(b_var, cnt32)); // batch_var * batch_count (f32), :65
-                const double m2 = s_var[j] * count + m_b + f64_div(delta * delta * count * n_b, totc);
+                const double m2 = __dadd_rn(__dadd_rn(__dmul_rn(s_var[j], count), m_b),
+                                            f64_div(__dmul_rn(__dmul_rn(__dmul_rn(delta, delta), count), n_b), totc));
                 st->ed_var[j] = f64_div(m2, totc);
             }
         }

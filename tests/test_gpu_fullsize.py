@@ -185,8 +185,11 @@ def test_soak_dynamic_vs_static_schedule_bit_identical(cuda_device, monkeypatch)
     dyn.close(); sta.close()
 
 
-def test_back_to_back_steps_overlap_vs_oracle(cuda_device):
-    """40 steps enqueued back to back (no host synchronisation in between) at a shape that takes the
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_back_to_back_steps_overlap_vs_oracle(cuda_device, pipelined):
+    """(pipelined=True: the same through ngu_epi_step_pipelined - each scan STREAMS while the previous epilogue is
+    still appending and takes the slot being appended from the previous q.)
+    40 steps enqueued back to back (no host synchronisation in between) at a shape that takes the
     dynamic schedule: every scan is programmatically launched behind the previous epilogue and prefetches
     its first tiles into L2 while that epilogue is still appending - the appended rows (cursor 0..39, i.e.
     inside prefetched tiles) must nevertheless be seen by the following steps.  Every step's rewards are
@@ -204,10 +207,14 @@ def test_back_to_back_steps_overlap_vs_oracle(cuda_device):
     al = (1.0 + 2.0 * rng.standard_normal((steps, B))).astype(np.float32)
     q_dev, a_dev = torch.from_numpy(qs).cuda(), torch.from_numpy(al).cuda()
     out = torch.empty(steps, B, device="cuda")
+    epi = torch.empty(steps, B, device="cuda")
     torch.cuda.synchronize()
     for t in range(steps):                                # enqueue only
-        r_int, _ = eng.step(q_dev[t], a_dev[t])
-        out[t].copy_(r_int)
+        if pipelined:                                     # (nothing else may be enqueued between pipelined steps)
+            eng.step(q_dev[t], a_dev[t], pipelined=True, out=(out[t], epi[t]))
+        else:
+            r_int, _ = eng.step(q_dev[t], a_dev[t])
+            out[t].copy_(r_int)
     torch.cuda.synchronize()
     got = out.cpu().numpy()
     orc = EpisodicOracle(B, N, k=k, use_c_scan=True)
@@ -221,3 +228,36 @@ def test_back_to_back_steps_overlap_vs_oracle(cuda_device):
     np.testing.assert_allclose(st["ed_mean"], orc.ed_rms.mean, rtol=1e-6)
     assert st["exchange_timeouts"] == 0 and st["cursor"] == steps
     eng.close()
+
+
+def test_256x30k_pipelined_equals_ordinary_bitwise(cuda_device):
+    """The headline shape (dynamic schedule, 296 CTAs, 983 MB): 10 steps through ngu_epi_step and through
+    ngu_epi_step_pipelined give identical reward bits, k-NN lists, memory and statistics."""
+    from ngu_b200.engine import EpisodicEngine
+    B, N, T = 256, 30000, 10
+    g = torch.Generator(device="cuda").manual_seed(3)
+    mem = torch.randn(B, N, 32, device="cuda", generator=g)
+    qs = torch.randn(T, B, 32, device="cuda", generator=g) * 2.0
+    al = 1.0 + torch.randn(T, B, device="cuda", generator=g)
+    res = []
+    for pipelined in (False, True):
+        eng = EpisodicEngine(B, N, device=0)
+        eng._memory.copy_(mem)
+        r = torch.empty(T, B, device="cuda")
+        e = torch.empty(T, B, device="cuda")
+        torch.cuda.synchronize()
+        for t in range(T):
+            eng.step(qs[t], al[t], pipelined=pipelined, out=(r[t], e[t]))
+        torch.cuda.synchronize()
+        st = eng.get_state()
+        d2, idx = eng.topk()
+        res.append((r.cpu().numpy(), e.cpu().numpy(), d2, idx, st, eng._memory[:, :T + 1].cpu().numpy()))
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+    a, b = res
+    assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    assert np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32)) and np.array_equal(a[3], b[3])
+    assert np.array_equal(a[5], b[5])
+    assert np.array_equal(a[4]["ed_mean"], b[4]["ed_mean"]) and a[4]["cursor"] == b[4]["cursor"] == T
+    assert a[4]["exchange_timeouts"] == b[4]["exchange_timeouts"] == 0
