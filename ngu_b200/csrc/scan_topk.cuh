@@ -903,6 +903,9 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
     if (p.pipe) {
         u64 w = 0ull;
         if (lane == 0) {
+            // both words in one round trip: the cursor word (valid whatever the epilogues are doing) is requested first,
+            // the acquire load behind it
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p.scan_cursor) : "memory");
             if (p.wait_epi != 0u) {
                 unsigned int v;
                 int polls = 0;
@@ -912,7 +915,6 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
                     if (++polls > kLLSpinLimit) { atomicAdd(p.timeouts, 1ull); break; }
                 }
             }
-            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p.scan_cursor) : "memory");
         }
         w = __shfl_sync(kFull, w, 0);
         const uint32_t ws = static_cast<uint32_t>(w >> 32);
