@@ -159,9 +159,19 @@ class EpisodicEngine:
         ``out=(r_int, r_epi)``: write the rewards there instead of the engine's own pair of buffers."""
         self._version += 1
         qk = self._q(q)
+        a_in = alpha
         if alpha is not None:
             alpha = alpha.to(device=self.device, dtype=torch.float32).contiguous()
+        if pipelined and (qk is not q or (alpha is not None and alpha.data_ptr() != a_in.data_ptr())):
+            # an input had to be converted: that copy is work enqueued between the two steps, and its result is not
+            # "ready before the previous step" - the pipelined contract does not hold, launch the ordinary way
+            pipelined = False
         r_int, r_epi = out if out is not None else (self._r_int, self._r_epi)
+        if out is not None:
+            for r in out:
+                if r is not None and (r.device != self.device or r.dtype != torch.float32 or not r.is_contiguous()
+                                      or r.numel() != self.n_actors):
+                    raise ValueError("out tensors must be contiguous float32 device tensors of n_actors elements")
         fn = self._lib.ngu_epi_step_pipelined if pipelined else self._lib.ngu_epi_step
         check(fn(self._h, _ptr(qk), _ptr(alpha), _ptr(r_int), _ptr(r_epi), self._stream()), self._h)
         self._q_keep2, self._q_keep = getattr(self, "_q_keep", None), qk      # the previous q outlives this step

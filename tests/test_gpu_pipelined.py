@@ -159,3 +159,35 @@ def test_pipelined_long_run_256x300(cuda_device):
     assert np.array_equal(eng.dump_memory(), orc.memory)
     assert eng.get_state()["exchange_timeouts"] == 0
     eng.close()
+
+
+def test_pipelined_with_inputs_that_need_conversion_falls_back(cuda_device):
+    """Inputs the engine has to convert (float64, non-contiguous) are produced by a copy enqueued between the steps:
+    the pipelined contract does not hold, so the engine launches those steps the ordinary way - same results."""
+    import torch
+    from ngu_b200.engine import EpisodicEngine
+    from oracle.episodic_oracle import EpisodicOracle
+    B, N, T = 12, 1500, 20
+    rng = np.random.default_rng(8)
+    orc = EpisodicOracle(B, N)
+    eng = EpisodicEngine(B, N, device=0)
+    qs = rng.standard_normal((T, B, 32), dtype=np.float32)
+    al = (1 + rng.standard_normal((T, B))).astype(np.float32)
+    q64 = torch.from_numpy(qs.astype(np.float64)).cuda()                 # dtype conversion needed
+    wide = torch.zeros(T, B, 64, device="cuda")
+    wide[:, :, ::2] = torch.from_numpy(qs).cuda()                        # non-contiguous view
+    a_dev = torch.from_numpy(al).cuda()
+    q32 = torch.from_numpy(qs).cuda()
+    r = torch.empty(T, B, device="cuda")
+    e = torch.empty(T, B, device="cuda")
+    torch.cuda.synchronize()
+    for t in range(T):
+        q = q64[t] if t % 3 == 0 else (wide[t, :, ::2] if t % 3 == 1 else q32[t])      # every third step is truly pipelined
+        eng.step(q, a_dev[t], pipelined=True, out=(r[t], e[t]))
+    torch.cuda.synchronize()
+    got = r.cpu().numpy()
+    for t in range(T):
+        want = orc.step(qs[t], al[t])
+        assert _rel(got[t].astype(np.float64), want["reward"]).max() <= REL_TOL, f"step {t}"
+    assert np.array_equal(eng.dump_memory(), orc.memory)
+    eng.close()
