@@ -100,6 +100,19 @@ SEQ_SYMBOLS = {
     "ngu_seq_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
+# exactly the symbols include/ngu_ar.h declares
+AR_HANDLE_BYTES = 128
+AR_SYMBOLS = {
+    "ngu_ar_create": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(_P)]),
+    "ngu_ar_destroy": (None, [_P]),
+    "ngu_ar_last_error": (C.c_char_p, [_P]),
+    "ngu_ar_buffer": (C.c_int, [_P, C.POINTER(_P)]),
+    "ngu_ar_export": (C.c_int, [_P, _P]),
+    "ngu_ar_connect": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "ngu_ar_allreduce_avg": (C.c_int, [_P, _P]),
+    "ngu_ar_timeouts": (C.c_int64, [_P]),
+}
+
 _lib = None
 
 
@@ -117,7 +130,7 @@ def load() -> C.CDLL:
             f"{LIB_PATH} is missing. Build it with `python -m ngu_b200.build` "
             "(or __graft_entry__.build()). ngu_b200 has no CPU / PyTorch fallback.")
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in list(SYMBOLS.items()) + list(SEQ_SYMBOLS.items()):
+    for name, (res, args) in list(SYMBOLS.items()) + list(SEQ_SYMBOLS.items()) + list(AR_SYMBOLS.items()):
         fn = getattr(lib, name)          # AttributeError if the ABI is out of date
         fn.restype = res
         fn.argtypes = args

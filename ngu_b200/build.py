@@ -13,9 +13,9 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libngu_epi.so")
-SOURCES = ["ngu_epi.cu", "ngu_seq.cu"]
+SOURCES = ["ngu_epi.cu", "ngu_seq.cu", "ngu_ar.cu"]
 HEADERS = ["scan_topk.cuh", "epilogue.cuh", "warp_topk.cuh", "p2p_exchange.cuh",
-           os.path.join("..", "..", "include", "ngu_epi.h"), os.path.join("..", "..", "include", "ngu_seq.h")]
+           os.path.join("..", "..", "include", "ngu_epi.h"), os.path.join("..", "..", "include", "ngu_seq.h"), os.path.join("..", "..", "include", "ngu_ar.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -37,12 +37,62 @@ import torch
 import torch.distributed as dist
 
 
+class _P2PBucket:
+    """One flat bucket in a buffer libngu_epi allocates and the peer ranks map over CUDA IPC (include/ngu_ar.h)."""
+
+    def __init__(self, numel, device, group):
+        import ctypes as C
+        from . import _cabi
+        from .engine import _DevArray
+        self._C, self._lib = C, _cabi.load()
+        h = C.c_void_p()
+        self._check(self._lib.ngu_ar_create(int(numel), device.index, C.byref(h)), None)
+        self._h = h
+        ptr = C.c_void_p()
+        self._check(self._lib.ngu_ar_buffer(self._h, C.byref(ptr)), self._h)
+        self.flat = torch.as_tensor(_DevArray(ptr.value, (int(numel),), "<f4"), device=device)
+        mine = C.create_string_buffer(_cabi.AR_HANDLE_BYTES)
+        self._check(self._lib.ngu_ar_export(self._h, mine), self._h)
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        handles = [None] * world
+        dist.all_gather_object(handles, mine.raw, group=group)
+        self._check(self._lib.ngu_ar_connect(self._h, rank, world, b"".join(handles)), self._h)
+        dist.barrier(group=group)
+
+    def _check(self, rc, h):
+        if rc != 0:
+            msg = self._lib.ngu_ar_last_error(h)
+            raise RuntimeError(f"libngu_epi (ngu_ar) error {rc}: {msg.decode() if msg else '?'}")
+
+    def allreduce_avg(self, stream):
+        self._check(self._lib.ngu_ar_allreduce_avg(self._h, self._C.c_void_p(stream.cuda_stream)), self._h)
+
+    def timeouts(self):
+        return int(self._lib.ngu_ar_timeouts(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.flat = None
+            self._lib.ngu_ar_destroy(self._h)
+            self._h = None
+
+
 class GradAllReducer:
-    def __init__(self, params, group=None, bucket_bytes=64 << 20, overlap=False):
+    def __init__(self, params, group=None, bucket_bytes=64 << 20, overlap=False, transport="nccl"):
+        """``transport``: "nccl" (default; north_star: NCCL over NVLink - or whatever backend the process group has) or
+        "p2p": the library's own all-reduce kernel over NVLink peer memory (include/ngu_ar.h; one process per GPU,
+        at most 8 ranks on one box, float32 CUDA parameters): one pass, each element crosses NVLink once in and once
+        out, result bit-identical on all ranks."""
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.overlap = overlap and self.world > 1
+        self.transport = transport if self.world > 1 else "nccl"
+        if self.transport not in ("nccl", "p2p"):
+            raise ValueError("transport must be 'nccl' or 'p2p'")
+        if self.transport == "p2p" and (self.world > 8 or any(p.dtype != torch.float32 or p.device.type != "cuda" for p in self.params)):
+            raise ValueError("transport='p2p' needs float32 CUDA parameters and at most 8 ranks")
+        self._p2p = []
         self._avg_native = (dist.is_initialized() and dist.get_backend(group) == "nccl")   # gloo has no AVG
         # buckets in reverse order: autograd finishes the last layers first
         self.buckets = []          # list of (flat tensor, [params], [views])
@@ -69,7 +119,14 @@ class GradAllReducer:
                     self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
 
     def _close(self, ps):
-        flat = torch.zeros(sum(p.numel() for p in ps), dtype=ps[0].dtype, device=ps[0].device)
+        numel = sum(p.numel() for p in ps)
+        if self.transport == "p2p":
+            pb = _P2PBucket(numel, ps[0].device, self.group)
+            self._p2p.append(pb)
+            flat = pb.flat
+        else:
+            self._p2p.append(None)
+            flat = torch.zeros(numel, dtype=ps[0].dtype, device=ps[0].device)
         views, off = [], 0
         for p in ps:
             v = flat[off:off + p.numel()].view_as(p)
@@ -126,6 +183,15 @@ class GradAllReducer:
     def _launch(self, bi):
         flat = self.buckets[bi][0]
         self._adopt(bi)
+        if self.transport == "p2p":
+            cur = torch.cuda.current_stream(flat.device)
+            if self._stream is not None:
+                self._stream.wait_stream(cur)
+                self._p2p[bi].allreduce_avg(self._stream)
+            else:
+                self._p2p[bi].allreduce_avg(cur)
+            self._pending.append((bi, None))
+            return
         if self._stream is not None:
             self._stream.wait_stream(torch.cuda.current_stream(flat.device))
             with torch.cuda.stream(self._stream):
@@ -144,33 +210,53 @@ class GradAllReducer:
             if bi not in launched:
                 self._launch(bi)
         for bi, work in self._pending:
-            work.wait()
+            if work is not None:
+                work.wait()
             flat = self.buckets[bi][0]
             if self._stream is not None:
                 torch.cuda.current_stream(flat.device).wait_stream(self._stream)
-            if not self._avg_native:
+            if work is not None and not self._avg_native:
                 flat.div_(self.world)
         self._pending.clear()
         self._ready.clear()
 
     finish = __call__
 
+    def p2p_timeouts(self):
+        """Barriers of the p2p transport that gave up waiting for a peer (must be 0; synchronises)."""
+        return sum(pb.timeouts() for pb in self._p2p if pb is not None)
+
     def close(self):
         for h in self._hooks:
             h.remove()
         self._hooks.clear()
+        if any(pb is not None for pb in self._p2p):
+            # the parameters' .grad are views of library-owned memory: detach them before it is freed
+            for flat, ps, views in self.buckets:
+                for p, v in zip(ps, views):
+                    if p.grad is v:
+                        p.grad = None
+            self.buckets = []
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier(group=self.group)      # nobody unmaps a bucket a peer's kernel may still touch
+            for pb in self._p2p:
+                if pb is not None:
+                    pb.close()
+            self._p2p = []
 
 
-def attach_learner_allreduce(intrinsic_novelty, group=None, overlap=False):
+def attach_learner_allreduce(intrinsic_novelty, group=None, overlap=False, transport="nccl"):
     """Install reducers on the two intrinsic-novelty learners of this package (embedding + RND)."""
     emb = intrinsic_novelty.epi_novel.embedding
     rnd = intrinsic_novelty.ll_novel
-    emb.grad_hook = GradAllReducer(list(emb.parameters()), group, overlap=overlap)
-    rnd.grad_hook = GradAllReducer(list(rnd.predictor.parameters()), group, overlap=overlap)
+    emb.grad_hook = GradAllReducer(list(emb.parameters()), group, overlap=overlap, transport=transport)
+    rnd.grad_hook = GradAllReducer(list(rnd.predictor.parameters()), group, overlap=overlap, transport=transport)
     return emb.grad_hook, rnd.grad_hook
 
 
-def attach_r2d2_allreduce(learner, group=None, overlap=True):
+def attach_r2d2_allreduce(learner, group=None, overlap=True, transport="nccl"):
     """The third seam: ``R2D2Learner.step`` (ngu/models/r2d2/r2d2_learner.py:44-58).
 
     ``learner`` is the reference's ``R2D2Learner`` (or anything with its attributes: ``policy``, ``optimizer``,
@@ -189,7 +275,8 @@ def attach_r2d2_allreduce(learner, group=None, overlap=True):
     """
     import torch.nn as nn
     params = list(learner.policy.parameters())
-    learner.grad_reducer = GradAllReducer(params, group, bucket_bytes=(20 << 20) if overlap else (64 << 20), overlap=overlap)
+    learner.grad_reducer = GradAllReducer(params, group, bucket_bytes=(20 << 20) if overlap else (64 << 20), overlap=overlap,
+                                          transport=transport)
 
     def step(self, td_errors, weights):
         loss = (td_errors.pow(2).mean(dim=0) * weights).mean()                       # r2d2_learner.py:51

@@ -147,3 +147,18 @@ def test_r2d2_seam_patch_single_process():
     for p, q in zip(a.policy.parameters(), b.policy.parameters()):
         assert torch.allclose(p, q, rtol=1e-6, atol=1e-7)
     assert a.update_count == 2 and a.logged[-1][0] == "R2D2Loss"
+
+
+def test_ngu_ar_header_symbols_are_exported():
+    """include/ngu_ar.h (the library's own NVLink all-reduce transport): every declared entry point is exported and bound."""
+    import os
+    import re
+    from ngu_b200 import _cabi
+    from tests.conftest import ROOT
+    lib = _cabi.load()
+    header = open(os.path.join(ROOT, "include", "ngu_ar.h")).read()
+    declared = set(re.findall(r"\b(ngu_ar_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_cabi.AR_SYMBOLS), declared ^ set(_cabi.AR_SYMBOLS)
+    for name in declared:
+        getattr(lib, name)
+    assert int(re.search(r"#define NGU_AR_HANDLE_BYTES (\d+)", header).group(1)) == _cabi.AR_HANDLE_BYTES

@@ -96,10 +96,13 @@ def main():
     full = [p.grad.detach().clone() for p in params]
     result = {"world": world, "params": n_params, "bytes": n_params * 4}
 
-    for overlap in (False, True):
+    modes = [("blocking", False, "nccl"), ("overlap", True, "nccl")]
+    if cuda:                                            # the library's own NVLink all-reduce kernel (include/ngu_ar.h)
+        modes += [("p2p_blocking", False, "p2p"), ("p2p_overlap", True, "p2p")]
+    for key, overlap, transport in modes:
         learner, hy = build_learner()
         params = list(learner.policy.parameters())
-        red = attach_r2d2_allreduce(learner, overlap=overlap)
+        red = attach_r2d2_allreduce(learner, overlap=overlap, transport=transport)
         # the gradient the patched step produces, captured before the optimiser consumes it
         grads = {}
         orig = learner.optimizer.step
@@ -124,21 +127,23 @@ def main():
             dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
             dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
             same &= bool(torch.equal(lo_, hi_))
-        key = "overlap" if overlap else "blocking"
         result[key] = {"worst_rel_vs_full_batch": float(t.item()), "identical_across_ranks": same,
                        "copies_in_steady_state": red.copies_in, "buckets": len(red.buckets),
-                       "update_count": learner.update_count}
+                       "update_count": learner.update_count, "transport": transport}
         assert t.item() < 2e-4, (key, t.item())
         assert same and red.copies_in == 0
+        if transport == "p2p":
+            assert red.p2p_timeouts() == 0
+        del ident, grads
         red.close()
 
     torch.backends.cudnn.allow_tf32 = True
     # ---- timing: does the all-reduce hide behind backward? ----
-    def timed(mode, iters=20 if cuda else 1):
+    def timed(mode, iters=20 if cuda else 1, transport="nccl"):
         learner, hy = build_learner()
         params = list(learner.policy.parameters())
         red = GradAllReducer(params, bucket_bytes=(20 << 20) if mode == "overlap" else (64 << 20),
-                             overlap=(mode == "overlap")) if mode != "none" else None
+                             overlap=(mode == "overlap"), transport=transport) if mode != "none" else None
         Tt, Bl = 16, 32
         o = torch.randn(Tt, Bl, 1, 84, 84, device=dev)
         a = torch.randint(0, 18, (Tt, Bl), device=dev)
@@ -170,13 +175,17 @@ def main():
         return float(t.item())
     result["backward_ms"] = {"backward_only": round(timed("none"), 3), "backward_plus_blocking_allreduce": round(timed("blocking"), 3),
                              "backward_plus_overlapped_allreduce": round(timed("overlap"), 3),
+                             **({"backward_plus_blocking_p2p_allreduce": round(timed("blocking", transport="p2p"), 3)} if cuda else {}),
                              "what": "reference DuelingLSTM, 16-step unroll, 32 sequences per rank; max over ranks"}
 
     # ---- raw bus bandwidth of the three buckets (gradients already in place: one ncclAllReduce(avg) each) ----
     bw = {}
-    for name, n in {"embedding": 182866, "rnd_predictor": 473376, "r2d2": 8188595}.items():
+    cases = [(name, n, "nccl") for name, n in {"embedding": 182866, "rnd_predictor": 473376, "r2d2": 8188595}.items()]
+    if cuda:
+        cases += [(name + "_p2p", n, "p2p") for name, n, _ in list(cases)]
+    for name, n, transport in cases:
         ps = [torch.nn.Parameter(torch.zeros(n, device=dev))]
-        red = GradAllReducer(ps)
+        red = GradAllReducer(ps, transport=transport)
         for _ in range(10):
             red()
         sync()
@@ -195,7 +204,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         bw[name] = {"bytes": n * 4, "ms": round(ms, 4), "algbw_GBs": round(n * 4 / ms / 1e6, 1),
-                    "busbw_GBs": round(n * 4 / ms / 1e6 * 2 * (world - 1) / world, 1)}
+                    "busbw_GBs": round(n * 4 / ms / 1e6 * 2 * (world - 1) / world, 1), "transport": transport}
+        # correctness of this very buffer: rank-dependent values -> their mean, on every rank
+        ps[0].grad.fill_(float(rank + 1))
+        red()
+        sync()
+        assert torch.allclose(ps[0].grad, torch.full_like(ps[0].grad, (world + 1) / 2)), name
+        red.close()
     result["allreduce"] = bw
     if rank == 0:
         print(json.dumps({"learner_dp_check": result}), flush=True)
