@@ -15,6 +15,7 @@ namespace {
 
 constexpr int kArMaxWorld = 8;
 constexpr int kArThreads = 512;
+constexpr int kFlagStride = 16;                       // u64 words between the two phases' flag rows: separate 128-byte lines
 constexpr long long kArSpinBudget = 4000000000ll;   // ~2 s
 
 thread_local std::string g_ar_create_error;
@@ -31,7 +32,7 @@ __device__ __forceinline__ void ar_st_flag(unsigned long long* p, unsigned long 
 }
 __device__ __forceinline__ unsigned long long ar_ld_flag(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ float4 ar_ld4(const float4* p) {
@@ -46,7 +47,7 @@ __device__ __forceinline__ void ar_st4(float4* p, float4 v) {
 // threads 0 .. world-1 each wait for one peer's flag of `phase`; returns (to all threads) after a CTA barrier
 __device__ __forceinline__ void ar_wait_all(const ArView& v, int phase, unsigned long long seq, unsigned long long* timeouts) {
     if (threadIdx.x < v.world) {
-        const unsigned long long* f = v.flags[v.rank] + phase * kArMaxWorld + threadIdx.x;
+        const unsigned long long* f = v.flags[v.rank] + phase * kFlagStride + threadIdx.x;
         const long long t0 = clock64();
         while (ar_ld_flag(f) < seq) {
             if (clock64() - t0 > kArSpinBudget) { atomicAdd(timeouts, 1ull); break; }
@@ -59,22 +60,51 @@ template <int WORLD>
 __global__ void __launch_bounds__(kArThreads) ar_allreduce_kernel(ArView v, unsigned long long seq, unsigned int* cta_ctr,
                                                                   unsigned long long* timeouts) {
     // ---- ready barrier: my gradients (written by earlier work on this stream) may be read, and nobody still reads or
-    //      writes the previous round (its done barrier) ----
-    if (blockIdx.x == 0 && threadIdx.x < WORLD) ar_st_flag(v.flags[threadIdx.x] + 0 * kArMaxWorld + v.rank, seq);
-    ar_wait_all(v, 0, seq, timeouts);
+    //      writes the previous round (its done barrier).  Only CTA 0 talks to the peers; the other CTAs wait for a LOCAL
+    //      word it sets (hundreds of CTAs polling the line the peers' flag stores have to reach delay those stores) ----
+    unsigned long long* go = reinterpret_cast<unsigned long long*>(cta_ctr) + 2;     // own 8 bytes of the counter block
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < WORLD) ar_st_flag(v.flags[threadIdx.x] + 0 * kFlagStride + v.rank, seq);
+        ar_wait_all(v, 0, seq, timeouts);
+        if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(go), "l"(seq) : "memory");
+    } else {
+        if (threadIdx.x == 0) {
+            unsigned long long g;
+            const long long t0 = clock64();
+            do {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(g) : "l"(go) : "memory");
+            } while (g < seq && clock64() - t0 < kArSpinBudget);
+        }
+        __syncthreads();
+    }
     // ---- slice `rank`: sum over ranks in rank order, average, store into every rank's bucket ----
+    // U elements per thread and trip so that small worlds also keep ~8 remote 16-byte loads in flight per thread
+    constexpr int U = WORLD <= 2 ? 4 : (WORLD <= 4 ? 2 : 1);
     const long long base = static_cast<long long>(v.rank) * v.n4;
     const float inv = 1.0f / static_cast<float>(WORLD);
-    for (long long i = static_cast<long long>(blockIdx.x) * kArThreads + threadIdx.x; i < v.n4; i += static_cast<long long>(gridDim.x) * kArThreads) {
-        float4 x[WORLD];
+    const long long stride = static_cast<long long>(gridDim.x) * kArThreads;
+    for (long long i0 = static_cast<long long>(blockIdx.x) * kArThreads + threadIdx.x; i0 < v.n4; i0 += stride * U) {
+        float4 x[U][WORLD];
 #pragma unroll
-        for (int g = 0; g < WORLD; ++g) x[g] = ar_ld4(reinterpret_cast<const float4*>(v.bucket[g]) + base + i);   // all loads in flight
-        float4 a = x[0];
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < v.n4) {
 #pragma unroll
-        for (int g = 1; g < WORLD; ++g) { a.x += x[g].x; a.y += x[g].y; a.z += x[g].z; a.w += x[g].w; }
-        a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+                for (int g = 0; g < WORLD; ++g) x[u][g] = ar_ld4(reinterpret_cast<const float4*>(v.bucket[g]) + base + i);   // all loads in flight
+            }
+        }
 #pragma unroll
-        for (int g = 0; g < WORLD; ++g) ar_st4(reinterpret_cast<float4*>(v.bucket[g]) + base + i, a);
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < v.n4) {
+                float4 a = x[u][0];
+#pragma unroll
+                for (int g = 1; g < WORLD; ++g) { a.x += x[u][g].x; a.y += x[u][g].y; a.z += x[u][g].z; a.w += x[u][g].w; }
+                a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+#pragma unroll
+                for (int g = 0; g < WORLD; ++g) ar_st4(reinterpret_cast<float4*>(v.bucket[g]) + base + i, a);
+            }
+        }
     }
     // ---- done barrier: the last CTA of this rank tells the peers that its slice has landed everywhere, then waits
     //      for theirs: when the kernel completes the local bucket holds the whole average ----
@@ -87,7 +117,7 @@ __global__ void __launch_bounds__(kArThreads) ar_allreduce_kernel(ArView v, unsi
     __syncthreads();
     if (!s_last) return;
     if (threadIdx.x == 0) *cta_ctr = 0u;
-    if (threadIdx.x < WORLD) ar_st_flag(v.flags[threadIdx.x] + 1 * kArMaxWorld + v.rank, seq);
+    if (threadIdx.x < WORLD) ar_st_flag(v.flags[threadIdx.x] + 1 * kFlagStride + v.rank, seq);
     ar_wait_all(v, 1, seq, timeouts);
 }
 
@@ -106,7 +136,7 @@ struct ngu_ar {
     int device = 0;
     long long n_floats = 0, n_padded = 0;
     float* bucket = nullptr;
-    unsigned long long* flags = nullptr;        // [2][kArMaxWorld] + [1] timeouts at index 2 * kArMaxWorld
+    unsigned long long* flags = nullptr;        // [2 phases][kFlagStride] + the timeout counter behind them
     unsigned int* cta_ctr = nullptr;
     ArView view{};
     bool connected = false;
@@ -153,8 +183,8 @@ int ngu_ar_create(int64_t n_floats, int32_t device, ngu_ar** out) {
     if (e == cudaSuccess) h->sm_count = prop.multiProcessorCount;
     if (e == cudaSuccess) e = cudaMalloc(&h->bucket, h->n_padded * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(h->bucket, 0, h->n_padded * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&h->flags, (2 * kArMaxWorld + 2) * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(h->flags, 0, (2 * kArMaxWorld + 2) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&h->flags, (2 * kFlagStride + 2) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(h->flags, 0, (2 * kFlagStride + 2) * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&h->cta_ctr, 64);
     if (e == cudaSuccess) e = cudaMemset(h->cta_ctr, 0, 64);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -234,7 +264,7 @@ int ngu_ar_allreduce_avg(ngu_ar* h, void* stream) {
     const long long max_ctas = 2ll * h->sm_count;          // all co-resident: the done barrier's last CTA waits on peers only
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
-    unsigned long long* timeouts = h->flags + 2 * kArMaxWorld;
+    unsigned long long* timeouts = h->flags + 2 * kFlagStride;
     const dim3 grid(static_cast<unsigned>(ctas)), block(kArThreads);
     switch (h->view.world) {
 #define AR_CASE(W) case W: ar_allreduce_kernel<W><<<grid, block, 0, s>>>(h->view, seq, h->cta_ctr, timeouts); break;
@@ -252,7 +282,7 @@ int64_t ngu_ar_timeouts(ngu_ar* h) {
     ArDeviceGuard guard(h->device);
     unsigned long long t = 0;
     if (cudaDeviceSynchronize() != cudaSuccess ||
-        cudaMemcpy(&t, h->flags + 2 * kArMaxWorld, sizeof t, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        cudaMemcpy(&t, h->flags + 2 * kFlagStride, sizeof t, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return static_cast<int64_t>(t);
 }
 
