@@ -675,14 +675,17 @@ def learner_allreduce_leg(D, rank):
     from ngu_b200.learner_allreduce import GradAllReducer
     sets = {"embedding": 182866, "rnd_predictor": 473376, "r2d2": 8188595}     # parameter counts, SURVEY.md 2.2
     out = {}
-    for name, n in sets.items():
+    cases = [(name, n, "nccl") for name, n in sets.items()]
+    if world <= 8:
+        cases += [(name + "_p2p", n, "p2p") for name, n in sets.items()]       # the library's own NVLink kernel (include/ngu_ar.h)
+    for name, n, transport in cases:
         sizes, left = [], n
         while left > 0:
             s = min(left, 1_600_000)
             sizes.append(s)
             left -= s
         params = [torch.nn.Parameter(torch.zeros(s, device=D.dev)) for s in sizes]
-        red = GradAllReducer(params)
+        red = GradAllReducer(params, transport=transport)
         for p in params:
             p.grad.fill_(float(rank + 1))
         for _ in range(5):
@@ -703,7 +706,8 @@ def learner_allreduce_leg(D, rank):
         ok = all(torch.allclose(p.grad, torch.full_like(p, want)) for p in params)
         nbytes = n * 4
         out[name] = {"bytes": nbytes, "ms": round(ms, 4), "algbw_GBs": round(nbytes / ms / 1e6, 1),
-                     "busbw_GBs": round(nbytes / ms / 1e6 * 2 * (world - 1) / world, 1), "average_correct": bool(ok)}
+                     "busbw_GBs": round(nbytes / ms / 1e6 * 2 * (world - 1) / world, 1), "average_correct": bool(ok),
+                     "transport": transport}
         red.close()
     return out
 

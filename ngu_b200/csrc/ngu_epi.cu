@@ -414,6 +414,12 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
             return NGU_ECUDA;                                                                  \
         }                                                                                      \
     } while (0)
+    // the handle's GPU for the rest of this call; the caller's current device is put back on every way out
+    struct RestoreDevice {
+        int prev = -1;
+        ~RestoreDevice() { if (prev >= 0) cudaSetDevice(prev); }
+    } restore_device;
+    if (cudaGetDevice(&restore_device.prev) != cudaSuccess || restore_device.prev == cfg->device) restore_device.prev = -1;
     CREATE_TRY(cudaSetDevice(cfg->device));
     cudaDeviceProp prop;
     CREATE_TRY(cudaGetDeviceProperties(&prop, cfg->device));
