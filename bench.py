@@ -397,9 +397,11 @@ def measure_shape(D, sh, B, N, rank, local_rank, K, W, ramp, want_clocks=True, e
     # ---- e2e: host buffers through the C ABI (H2D + step + D2H, synchronous) ----
     host_call = world == 1 or sh.exchange == "p2p"   # the fused single-call step (exchange inside the epilogue kernel)
 
+    r_out = [np.empty((2, B), np.float32) for _ in range(2)]             # the caller's result buffers (rewards land here)
+
     def e2e_step(i):
         if host_call:
-            return eng.step_host(q_host[i % NQ], a_host[i % NQ])[0]       # pinned CPU tensors, passed by address
+            return eng.step_host(q_host[i % NQ], a_host[i % NQ], out=r_out[i & 1])[0]   # pinned CPU tensors, passed by address
         q = q_host[i % NQ].to(dev, non_blocking=True)
         a = a_host[i % NQ].to(dev, non_blocking=True)
         return sh.step(q, a)[0].cpu()

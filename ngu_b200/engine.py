@@ -227,13 +227,29 @@ class EpisodicEngine:
                 pass
         return ptr, keep
 
-    def step_host(self, q, alpha=None):
+    def step_host(self, q, alpha=None, out=None):
         """ngu_epi_step_host: host float32 buffers in (CPU torch tensors or numpy arrays; torch tensors are
-        the cheaper to pass), host float32 rewards (r_int, r_epi) out as fresh numpy arrays, synchronous.
+        the cheaper to pass), host float32 rewards (r_int, r_epi) out, synchronous.  The rewards are fresh numpy arrays
+        unless the caller passes ``out``: a C-contiguous float32 numpy array of shape (2, n_actors) the library writes
+        into directly (rows r_int, r_epi are returned as views of it).
         Called back to back, the library keeps the next step's launches pre-armed on the GPU (include/ngu_epi.h)."""
         q_ptr, _q = self._host_ptr_cached(q, self._q_shape, "controllable state")
         a_ptr, _a = (None, None) if alpha is None else self._host_ptr_cached(alpha, self._a_shape, "alpha")
         self._version += 1
+        if out is not None:
+            e = self._hp_cache.get(id(out))
+            if e is None or e[1]() is not out:
+                if type(out) is not np.ndarray or out.dtype != np.float32 or out.shape != (2, self.n_actors) or not out.flags.c_contiguous:
+                    raise ValueError(f"out must be a C-contiguous float32 numpy array of shape (2, {self.n_actors})")
+                e = (out.ctypes.data, weakref.ref(out), True)
+                if len(self._hp_cache) >= 64:
+                    self._hp_cache.clear()
+                self._hp_cache[id(out)] = e
+            o_ptr = e[0]
+            rc = self._step_host_fn(self._h, q_ptr, a_ptr, o_ptr, o_ptr + 4 * self.n_actors)
+            if rc:
+                check(rc, self._h)
+            return out[0], out[1]
         rc = self._step_host_fn(self._h, q_ptr, a_ptr, self._out_ptr, self._out_ptr + 4 * self.n_actors)
         if rc:
             check(rc, self._h)

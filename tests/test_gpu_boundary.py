@@ -191,3 +191,23 @@ def test_pre_armed_host_steps_vs_oracle(cuda_device, monkeypatch, B, N):
     st = eng.get_state()
     assert st["exchange_timeouts"] == 0 and st["steps"] == T
     eng.close()
+
+
+def test_step_host_writes_into_the_callers_buffer(cuda_device):
+    """step_host(out=...): the rewards land in the caller's (2, B) array, no intermediate copy; same values."""
+    from ngu_b200.engine import EpisodicEngine
+    B, N = 9, 800
+    rng = np.random.default_rng(2)
+    mem0 = rng.standard_normal((N, B, 32), dtype=np.float32)
+    e1 = EpisodicEngine(B, N, device=0); e1.load_memory(mem0)
+    e2 = EpisodicEngine(B, N, device=0); e2.load_memory(mem0)
+    out = np.zeros((2, B), np.float32)
+    for t in range(6):
+        q = rng.standard_normal((B, 32), dtype=np.float32)
+        a = (1 + rng.standard_normal(B)).astype(np.float32)
+        r1, p1 = e1.step_host(q, a)
+        r2, p2 = e2.step_host(q, a, out=out)
+        assert r2.base is out and np.array_equal(r1, out[0]) and np.array_equal(p1, out[1])
+    with pytest.raises(ValueError):
+        e2.step_host(q, a, out=np.zeros((B, 2), np.float32))
+    e1.close(); e2.close()
