@@ -44,16 +44,19 @@ std::string fmt(const char* f, ...) {
 // Scan kernel variants (WARPS, STAGES, rows-per-lane); see DESIGN.md "kernel A".
 struct Variant {
     int warps, stages, rpl, ctas_per_sm;
-    const void* fn;
+    const void* fn;       // launched
+    const void* fn_dbg;   // flavour with the experiment switches / timeline stamps compiled in (NGU_EPI_DEBUG_SCAN, _TIMELINE)
     int smem;
 };
-template <int W, int S, int R>
+// LEAN: also instantiate the production flavour (no debug code in the streaming loop).  Only the default geometry has
+// one; the experiment geometries always run their debug-capable build.
+template <int W, int S, int R, bool LEAN = false>
 Variant make_variant(int ctas_per_sm) {
-    return Variant{W, S, R, ctas_per_sm, reinterpret_cast<const void*>(&scan_topk_kernel<W, S, R>),
-                   ScanCfg<W, S, R>::kSmemBytes};
+    return Variant{W, S, R, ctas_per_sm, reinterpret_cast<const void*>(&scan_topk_kernel<W, S, R, !LEAN>),
+                   reinterpret_cast<const void*>(&scan_topk_kernel<W, S, R, true>), ScanCfg<W, S, R>::kSmemBytes};
 }
 const Variant kVariants[] = {
-    make_variant<8, 3, 1>(2),   // 0 (default): 16 warps/SM, 3 x 4 KB ring per warp  = 192 KB in flight / SM
+    make_variant<8, 3, 1, true>(2),   // 0 (default): 16 warps/SM, 3 x 4 KB ring per warp  = 192 KB in flight / SM
     make_variant<8, 6, 1>(1),   // 1:  8 warps/SM, 6 x 4 KB                         = 192 KB
     make_variant<8, 3, 2>(1),   // 2:  8 warps/SM, 3 x 8 KB                         = 192 KB
     make_variant<16, 3, 1>(1),  // 3: 16 warps/SM in one CTA, 3 x 4 KB              = 192 KB
@@ -440,6 +443,7 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
         return NGU_EINVAL;
     }
     CREATE_TRY(cudaFuncSetAttribute(h->var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->var.smem));
+    if (h->var.fn_dbg != h->var.fn) CREATE_TRY(cudaFuncSetAttribute(h->var.fn_dbg, cudaFuncAttributeMaxDynamicSharedMemorySize, h->var.smem));
     CREATE_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(&epilogue_kernel<kEpilogueThreads>),
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kEpilogueStageBytes)));
     if (const char* e = getenv("NGU_EPI_PDL")) h->use_pdl = atoi(e) != 0;
@@ -458,6 +462,7 @@ int ngu_epi_create(const ngu_epi_cfg* cfg, float* memory_dev, ngu_epi** out) {
         }
     }
     if (const char* e = getenv("NGU_EPI_DEBUG_SCAN")) h->debug_scan = atoi(e);
+    if (h->debug_scan != 0 || h->timeline != nullptr) h->var.fn = h->var.fn_dbg;
     apply_sched_env(h);
     plan_geometry(h);
 

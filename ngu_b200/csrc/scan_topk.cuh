@@ -811,6 +811,17 @@ __device__ __forceinline__ float row_d2(uint32_t row_addr, uint32_t sw, const f2
     return h;
 }
 
+// Rare side loads of the producer lane (see produce()): query row + floor of a starting run, q_prev row of the slot
+// being appended by the previous step.  Out of line on purpose.
+__device__ __noinline__ void run_aux_loads(uint32_t aux, const float* q, const float* q_prev, const u64* floor_word, int actor,
+                                           uint32_t bar, bool run_start, bool hz) {
+    if (run_start) {
+        bulk_load(aux, q + static_cast<int64_t>(actor) * 32, 128, bar);
+        bulk_load(aux + 128, floor_word, 16, bar);
+    }
+    if (hz) bulk_load(aux + 144, q_prev + static_cast<int64_t>(actor) * 32, 128, bar);
+}
+
 template <int WARPS, int STAGES, int RPL>
 struct ScanCfg {
     static constexpr int kWarps = WARPS;
@@ -828,10 +839,15 @@ struct ScanCfg {
     static constexpr int kMaxCtasPerSm = (227 * 1024) / (kSmemBytes + 1024) > 0 ? (227 * 1024) / (kSmemBytes + 1024) : 1;
 };
 
-template <int WARPS, int STAGES, int RPL>
+// DBG = false: the production flavour.  The experiment switches (ScanParams::debug, NGU_EPI_DEBUG_SCAN) and the per-warp
+// timeline stamps are compiled out of the streaming loop - tested every tile they were ~20 of its ~255 instructions.
+// The host launches the DBG = true flavour whenever one of them is set (ngu_epi_create).
+template <int WARPS, int STAGES, int RPL, bool DBG>
 __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxCtasPerSm) scan_topk_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                 const ScanParams p) {
     using Cfg = ScanCfg<WARPS, STAGES, RPL>;
+    const int dbg = DBG ? p.debug : 0;
+    unsigned long long* const timeline = DBG ? p.timeline : nullptr;
     extern __shared__ uint8_t smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -851,7 +867,7 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
 
     const int gw = blockIdx.x * WARPS + warp;
     const int n_warps = gridDim.x * WARPS;
-    const unsigned long long tl0 = p.timeline ? globaltimer_ns() : 0ull;
+    const unsigned long long tl0 = timeline ? globaltimer_ns() : 0ull;
     unsigned long long tl1 = 0ull;
     const ScanSched& sc = p.sched;
     if (threadIdx.x == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(cta_area + WARPS * (2 * 32 * 8 + 2 * 8)), "r"(0u) : "memory");
@@ -873,7 +889,7 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
         // into L2: the CTA is resident but may not touch the memory's CONTENT before the grid dependency
         // resolves (the epilogue is appending a row) - a prefetch does not, and L2 being the coherence point
         // the real loads below still see that row.  ~28 MB of HBM traffic leave the step's critical path.
-        if (!(p.debug & 32)) {
+        if (!(dbg & 32)) {
             int fb = pb, fti = pti;
 #pragma unroll 1
             for (int s = 0; s < p.prefetch_tiles; ++s) {
@@ -979,13 +995,14 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
             const bool hz = pti == hz_tile;   // pipelined launch: the tile holds the slot the previous step is appending to
             mbar_expect_tx(bar, Cfg::kTileBytes + (run_start ? 144 : 0) + (hz ? 128 : 0));
             tma_load_2d(my_tiles + s * Cfg::kTileBytes, &tmap, 0, pb * N + pti * Cfg::kTileRows, bar, policy);
-            const uint32_t aux = my_aux + s * Cfg::kAuxBytes;
-            if (run_start) {           // the run's query row and floor travel with its first tile
-                bulk_load(aux, p.q + static_cast<int64_t>(pb) * 32, 128, bar);
-                bulk_load(aux + 128, actor_floor(p, pb), 16, bar);
+            // the run's query row and floor travel with its first tile, and so does the final content of the slot the
+            // previous step is appending to.  Both are rare (once per run / per actor) and sit behind a REAL branch:
+            // predicated, each bulk copy costs its address arithmetic and uniform-register hand-over on every tile
+            // (36 of the producer's 87 instructions per tile, ncu source page of r02f).
+            if (run_start || hz) {
+                run_aux_loads(my_aux + s * Cfg::kAuxBytes, p.q, p.q_prev, actor_floor(p, pb), pb, bar, run_start, hz);
                 last_pb = pb;
             }
-            if (hz) bulk_load(aux + 144, p.q_prev + static_cast<int64_t>(pb) * 32, 128, bar);   // that slot's final content
             ++pt;
             if (++pti == tpa) { pti = 0; ++pb; }
         } else {
@@ -1021,7 +1038,7 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
         asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(b), "=r"(ti) : "r"(my_desc + 8 * stage) : "memory");
         if (b < 0) break;
         if (b != cur) {
-            if (cur >= 0 && !(p.debug & 4)) {
+            if (cur >= 0 && !(dbg & 4)) {
                 if (static_sched && p.cta_merge) {
                     if (run_tiles == tpa) {            // this warp scanned the whole actor: final
                         write_knn(knn_out(p, cur), k, knn_flags(p), top.lkey, lane);
@@ -1048,7 +1065,7 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
         }
 
         mbar_wait(my_bars + 8 * stage, parity);
-        if (p.timeline && first) { tl1 = globaltimer_ns(); first = false; }
+        if (timeline && first) { tl1 = globaltimer_ns(); first = false; }
         if (run_start) {   // query row and floor arrived with the tile (same mbarrier)
             const uint32_t aux = my_aux + stage * Cfg::kAuxBytes;
 #pragma unroll
@@ -1056,13 +1073,13 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
             u64 fw;
             asm volatile("ld.shared.u64 %0, [%1];" : "=l"(fw) : "r"(aux + 128) : "memory");
             // keys at or below the actor's published floor cannot make the final top-k
-            top.reset((p.debug & 16) ? 0ull : floor_key(fw, tag));
+            top.reset((dbg & 16) ? 0ull : floor_key(fw, tag));
             run_start = false;
         }
         const uint32_t tile = my_tiles + stage * Cfg::kTileBytes;
         const int row0 = ti * Cfg::kTileRows;
         float d2[RPL];
-        if (p.debug & 2) {
+        if (dbg & 2) {
 #pragma unroll
             for (int i = 0; i < RPL; ++i) d2[i] = lds128(tile + static_cast<uint32_t>(lane + 32 * i) * 128u + (sw << 4)).x;
         } else {
@@ -1086,7 +1103,7 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
         for (int i = 0; i < RPL; ++i) {
             const int slot = row0 + lane + 32 * i;
             const u64 key = slot < N ? make_key(d2[i], static_cast<uint32_t>(slot), largest) : 0ull;
-            if (p.debug & 1) top.lkey ^= key; else
+            if (dbg & 1) top.lkey ^= key; else
             top.offer(key, lane, k);
         }
         ++run_tiles;
@@ -1097,22 +1114,22 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
         }
     }
 
-    const unsigned long long tl2 = p.timeline ? globaltimer_ns() : 0ull;
+    const unsigned long long tl2 = timeline ? globaltimer_ns() : 0ull;
     const int workers = n_warps < sc.n_chunks ? n_warps : sc.n_chunks;
-    unsigned long long* tl_rec = p.timeline ? p.timeline + static_cast<int64_t>(gw) * 8 : nullptr;
-    if (cur >= 0 && !(p.debug & 4) && static_sched && !p.cta_merge) {
+    unsigned long long* tl_rec = timeline ? timeline + static_cast<int64_t>(gw) * 8 : nullptr;
+    if (cur >= 0 && !(dbg & 4) && static_sched && !p.cta_merge) {
         u64 ret = 0ull;
         const bool last_partial = flush_run_static(p, cur, run_tiles, run_first, tag, top, lane, ret);
         if (pend_actor >= 0) finish_static(p, pend_actor, pend_n, pend_ret, tag, lane, my_tiles, tl_rec);
         if (last_partial) finish_static(p, cur, run_tiles, ret, tag, lane, my_tiles, tl_rec);
-    } else if (cur >= 0 && !(p.debug & 4) && static_sched) {
+    } else if (cur >= 0 && !(dbg & 4) && static_sched) {
         int last_actor = -1;
         if (run_tiles == tpa) write_knn(knn_out(p, cur), k, knn_flags(p), top.lkey, lane);
         else last_actor = cur;
         const int rest = sc.n_chunks - static_cast<int>(blockIdx.x) * WARPS;
         static_cta_finish<WARPS>(p, cta_area, warp, lane, tag, rest < WARPS ? rest : WARPS, pend_actor, pend_n, pend_key,
                                  last_actor, run_tiles, top.lkey, my_tiles, tl_rec);
-    } else if (cur >= 0 && !(p.debug & 4)) {
+    } else if (cur >= 0 && !(dbg & 4)) {
         if (pend_actor >= 0) complete_pending(p, pend_actor, pend_key, pend_n, pend_ret, tag, lane);
         if (flush_run(p, cur, run_tiles, tag, top, lane, pend_key, pend_n, pend_ret))
             complete_pending(p, cur, pend_key, pend_n, pend_ret, tag, lane);
@@ -1146,8 +1163,8 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
             p.sched_ctr[2] = next;
         }
     }
-    if (p.timeline && lane == 0) {
-        unsigned long long* o = p.timeline + static_cast<int64_t>(gw) * 8;
+    if (timeline && lane == 0) {
+        unsigned long long* o = timeline + static_cast<int64_t>(gw) * 8;
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         o[0] = tl0; o[1] = tl1; o[2] = tl2; o[3] = globaltimer_ns(); o[4] = smid;
