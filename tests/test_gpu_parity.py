@@ -328,3 +328,33 @@ def test_static_merge_levels_vs_oracle(cuda_device, monkeypatch, B, N, k, mode, 
     assert np.array_equal(eng.dump_memory(), orc.memory)
     assert eng.get_state()["exchange_timeouts"] == 0
     eng.close()
+
+
+@pytest.mark.parametrize("B,N", [(7, 2500), (40, 9000)])
+def test_debug_capable_kernel_flavour_vs_oracle(cuda_device, monkeypatch, B, N):
+    """The default scan geometry exists in two builds: the production one (experiment switches and timeline stamps
+    compiled out of the streaming loop) and the debug-capable one the library launches when NGU_EPI_DEBUG_TIMELINE /
+    NGU_EPI_DEBUG_SCAN is set.  Every other test runs the first; this one runs the second against the oracle and reads
+    the per-warp stamps it records."""
+    from ngu_b200.engine import EpisodicEngine
+    from oracle.episodic_oracle import EpisodicOracle
+    monkeypatch.setenv("NGU_EPI_DEBUG_TIMELINE", "1")
+    rng = np.random.default_rng(B + N)
+    mem0 = rng.standard_normal((N, B, 32), dtype=np.float32)
+    orc = EpisodicOracle(B, N)
+    orc.memory[...] = mem0
+    eng = EpisodicEngine(B, N, device=0)
+    eng.load_memory(mem0)
+    for t in range(4):
+        q = rng.standard_normal((B, 32), dtype=np.float32)
+        alpha = (1.0 + 2.0 * rng.standard_normal(B)).astype(np.float32)
+        ref = orc.step(q, alpha)
+        r_int, _ = eng.step_host(q, alpha)
+        d2, idx = eng.topk()
+        assert np.array_equal(idx.T, ref["idx"])
+        assert np.array_equal(d2.T.view(np.uint32), ref["d2"].view(np.uint32))
+        assert _rel(r_int.astype(np.float64), ref["reward"]).max() <= REL_TOL
+    tl = np.zeros((148 * 4 * 32, 8), np.uint64)
+    nw = eng._lib.ngu_epi_debug_timeline(eng._h, tl.ctypes.data, tl.shape[0])
+    assert nw > 0 and (tl[:nw, 0] > 0).any() and (tl[:nw, 3] >= tl[:nw, 0]).all()   # start <= end stamps of every warp
+    eng.close()
