@@ -784,12 +784,16 @@ __device__ __forceinline__ void f2_unpack(f2 v, float& lo, float& hi) { asm("mov
 
 // d^2 of one swizzled 128-byte row against the register-resident query (16 packed pairs).
 // row_addr = shared address of the row start, sw = row & 7, z = kNegZero2 from the parameters.
+// Rows are 128-byte aligned (tile rows; the q_prev rows of the aux area), so the chunk offset (c ^ sw) << 4 can be
+// XORed into the address: one LOP3 with an immediate per chunk from the base row_addr ^ (sw << 4), instead of a LOP3 and
+// an add per chunk.
 __device__ __forceinline__ float row_d2(uint32_t row_addr, uint32_t sw, const f2 (&q)[16], f2 z) {
     f2 a[4];   // lane accumulators (a0,a1) (a2,a3) (a4,a5) (a6,a7)
+    const uint32_t base = row_addr ^ (sw << 4);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         f2 m01, m23;
-        lds_2x64(row_addr + ((static_cast<uint32_t>(c) ^ sw) << 4), m01, m23);
+        lds_2x64(base ^ (static_cast<uint32_t>(c) << 4), m01, m23);
         const f2 s01 = f2_sq(f2_sub(m01, q[2 * c]), z);
         const f2 s23 = f2_sq(f2_sub(m23, q[2 * c + 1]), z);
         const int i = 2 * (c & 1);   // elements 4c..4c+3 feed lane accumulators 4(c&1)..4(c&1)+3
@@ -813,13 +817,13 @@ __device__ __forceinline__ float row_d2(uint32_t row_addr, uint32_t sw, const f2
 
 // Rare side loads of the producer lane (see produce()): query row + floor of a starting run, q_prev row of the slot
 // being appended by the previous step.  Out of line on purpose.
-__device__ __noinline__ void run_aux_loads(uint32_t aux, const float* q, const float* q_prev, const u64* floor_word, int actor,
-                                           uint32_t bar, bool run_start, bool hz) {
+__device__ __noinline__ void run_aux_loads(uint32_t aux, uint32_t qprev_row, const float* q, const float* q_prev, const u64* floor_word,
+                                           int actor, uint32_t bar, bool run_start, bool hz) {
     if (run_start) {
         bulk_load(aux, q + static_cast<int64_t>(actor) * 32, 128, bar);
         bulk_load(aux + 128, floor_word, 16, bar);
     }
-    if (hz) bulk_load(aux + 144, q_prev + static_cast<int64_t>(actor) * 32, 128, bar);
+    if (hz) bulk_load(qprev_row, q_prev + static_cast<int64_t>(actor) * 32, 128, bar);
 }
 
 template <int WARPS, int STAGES, int RPL>
@@ -829,11 +833,14 @@ struct ScanCfg {
     static constexpr int kTileRows = 32 * RPL;
     static constexpr int kTileBytes = kTileRows * 128;
     static constexpr int kThreads = WARPS * 32;
-    static constexpr int kAuxBytes = 128 + 16 + 128;   // per stage: query row + {floor, ctr} of the actor whose run starts there
-                                                       // + the row the previous step is appending (pipelined launches)
+    // per warp: STAGES rows for the slot the previous step is appending (pipelined launches; 128-byte aligned like tile
+    // rows: row_d2), then per stage the query row + {floor, ctr} of the actor whose run starts there
+    static constexpr int kRunAuxBytes = 128 + 16;
+    static constexpr int kWarpAuxBytes = (STAGES * (128 + kRunAuxBytes) + 127) / 128 * 128;
+    static_assert((WARPS * STAGES * 16) % 128 == 0, "barriers + descriptors must keep the aux blocks 128-byte aligned");
     // tiles + 1024 B alignment slack + barriers + per-stage descriptors + per-stage run-start data
     static constexpr int kCtaMergeBytes = WARPS * (2 * 32 * 8 + 2 * 8) + 16;   // static schedules: the CTA-level combine
-    static constexpr int kSmemBytes = WARPS * STAGES * kTileBytes + 1024 + WARPS * STAGES * (16 + kAuxBytes) + kCtaMergeBytes;
+    static constexpr int kSmemBytes = WARPS * STAGES * kTileBytes + 1024 + WARPS * STAGES * 16 + WARPS * kWarpAuxBytes + kCtaMergeBytes;
     // CTAs per SM the shared memory allows (227 KB per SM): tells ptxas how many registers it may use.
     // Without it ptxas squeezes the kernel into 80 registers and spills producer state in the hot loop.
     static constexpr int kMaxCtasPerSm = (227 * 1024) / (kSmemBytes + 1024) > 0 ? (227 * 1024) / (kSmemBytes + 1024) : 1;
@@ -860,10 +867,11 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
     const uint32_t my_tiles = tiles0 + warp * STAGES * Cfg::kTileBytes;
     const uint32_t my_bars = bars0 + warp * STAGES * 8;
     const uint32_t my_desc = desc0 + warp * STAGES * 8;   // per stage {actor, tile in actor}; actor < 0: no more work
-    const uint32_t aux0 = desc0 + WARPS * STAGES * 8;     // 16-byte aligned: everything before it is a multiple of 16
-    const uint32_t my_aux = aux0 + warp * STAGES * Cfg::kAuxBytes;
+    const uint32_t aux0 = desc0 + WARPS * STAGES * 8;     // 128-byte aligned (static_assert in ScanCfg)
+    const uint32_t my_qprev = aux0 + warp * Cfg::kWarpAuxBytes;      // this warp's block: q_prev rows, one per stage,
+    const uint32_t my_aux = my_qprev + STAGES * 128;                 // then query row + floor per stage
 
-    const uint32_t cta_area = aux0 + WARPS * STAGES * Cfg::kAuxBytes;   // static schedules: lists, meta, arrival counter
+    const uint32_t cta_area = aux0 + WARPS * Cfg::kWarpAuxBytes;   // static schedules: lists, meta, arrival counter
 
     const int gw = blockIdx.x * WARPS + warp;
     const int n_warps = gridDim.x * WARPS;
@@ -1000,7 +1008,7 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
             // predicated, each bulk copy costs its address arithmetic and uniform-register hand-over on every tile
             // (36 of the producer's 87 instructions per tile, ncu source page of r02f).
             if (run_start || hz) {
-                run_aux_loads(my_aux + s * Cfg::kAuxBytes, p.q, p.q_prev, actor_floor(p, pb), pb, bar, run_start, hz);
+                run_aux_loads(my_aux + s * Cfg::kRunAuxBytes, my_qprev + s * 128, p.q, p.q_prev, actor_floor(p, pb), pb, bar, run_start, hz);
                 last_pb = pb;
             }
             ++pt;
@@ -1067,7 +1075,7 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
         mbar_wait(my_bars + 8 * stage, parity);
         if (timeline && first) { tl1 = globaltimer_ns(); first = false; }
         if (run_start) {   // query row and floor arrived with the tile (same mbarrier)
-            const uint32_t aux = my_aux + stage * Cfg::kAuxBytes;
+            const uint32_t aux = my_aux + stage * Cfg::kRunAuxBytes;
 #pragma unroll
             for (int c = 0; c < 8; ++c) lds_2x64(aux + 16 * c, q[2 * c], q[2 * c + 1]);
             u64 fw;
@@ -1088,7 +1096,7 @@ __global__ void __launch_bounds__(WARPS * 32, ScanCfg<WARPS, STAGES, RPL>::kMaxC
             for (int i = 0; i < RPL; ++i) {
                 uint32_t ra = tile + static_cast<uint32_t>(lane + 32 * i) * 128u, rs = sw;
                 if (hz && lane + 32 * i == hz_row) {   // the slot being appended: its content from q_prev (linear, not swizzled)
-                    ra = my_aux + stage * Cfg::kAuxBytes + 144;
+                    ra = my_qprev + stage * 128;
                     rs = 0u;
                 }
                 d2[i] = row_d2(ra, rs, q, p.neg_zero2);

@@ -25,6 +25,11 @@ def run(B, N, env, steps=600):
     for i in range(steps): eng.step(qs[i % 8], al[i % 8])
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / steps * 1e3
+    for i in range(50): eng.step(qs[i % 8], al[i % 8], pipelined=True)
+    e0.record()
+    for i in range(steps): eng.step(qs[i % 8], al[i % 8], pipelined=True)
+    e1.record(); torch.cuda.synchronize()
+    pipe_us = e0.elapsed_time(e1) / steps * 1e3
     eng.scan_timing_begin(200)
     for i in range(200): eng.step(qs[i % 8], al[i % 8])
     ms, n = eng.scan_timing_end()
@@ -41,7 +46,7 @@ def run(B, N, env, steps=600):
         for i in range(300): eng.step_host(qh[i % 8], ah[i % 8])
         host = min(host, (time.perf_counter() - t0) / 300 * 1e6)
     eng.close()
-    return dict(B=B, N=N, env=env, step_us=round(us, 2), scan_alone_us=round(ms / n * 1e3, 2), host_step_us=round(host, 2))
+    return dict(B=B, N=N, env=env, step_us=round(us, 2), pipelined_us=round(pipe_us, 2), scan_alone_us=round(ms / n * 1e3, 2), host_step_us=round(host, 2))
 
 if __name__ == "__main__":
     B, N, reps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
