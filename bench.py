@@ -719,6 +719,10 @@ def learner_allreduce_leg(D, rank):
 # ---------------------------------------------------------------------------------
 def run_gpu_arm(args, rank, world, local_rank):
     import torch
+    if not torch.cuda.is_available():
+        # no fallback on purpose: this arm measures the CUDA library and nothing else
+        raise SystemExit("bench.py: no CUDA device - the product path is libngu_epi.so on a B200 and has no CPU fallback "
+                         "(the CPU numbers are `--impl reference`)")
     torch.cuda.set_device(local_rank)
     D = Dist(world, local_rank)
     K, W = args.steps, args.warmup
