@@ -445,8 +445,21 @@ def stream_only_ms(B, N, local_rank, args, qs, gen):
     for i in range(100):
         bare.scan(qs[i % len(qs)])
     ms, n = bare.scan_timing_end()
+    # the same bare stream launched as software-pipelined steps (what `value` is timed with): the practical read-only
+    # ceiling of this access pattern when the stream never drains between launches
+    al = 1.0 + torch.zeros(B, device=qs[0].device)
+    for i in range(30):
+        bare.step(qs[i % len(qs)], al, pipelined=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(100):
+        bare.step(qs[i % len(qs)], al, pipelined=True)
+    e1.record()
+    torch.cuda.synchronize()
+    piped = e0.elapsed_time(e1) / 100
     bare.close()
-    return ms / max(n, 1)
+    return ms / max(n, 1), piped
 
 
 # ---------------------------------------------------------------------------------
@@ -747,10 +760,10 @@ def run_gpu_arm(args, rank, world, local_rank):
     geo = sh.engine.scan_geometry()
     exchange_mode = sh.exchange
 
-    stream_ms = None
+    stream_ms = stream_piped_ms = None
     if rank == 0 and not args.no_stream_only:
         try:
-            stream_ms = stream_only_ms(B, N, local_rank, args, m["qs"], m["gen"])
+            stream_ms, stream_piped_ms = stream_only_ms(B, N, local_rank, args, m["qs"], m["gen"])
         except Exception as e:                      # a diagnostic must never cost the bench line
             log(f"stream-only diagnostic skipped: {e}")
     sh.engine.close()
@@ -847,8 +860,12 @@ def run_gpu_arm(args, rank, world, local_rank):
                                       "stream never drains between launches, so the whole step can beat the kernel timed alone "
                                       "(and the copy-measured peak: the scan only reads)",
                          "stream_only_launch_ms": stream_ms,
+                         "stream_only_pipelined_ms_per_step": stream_piped_ms,
+                         "stream_only_pipelined_gbs": (bytes_per_query(N) * B / (stream_piped_ms / 1e3) / 1e9) if stream_piped_ms else None,
                          "stream_only_note": "same kernel, distance math / top-k / flush / merge switched off "
-                                             "(NGU_EPI_DEBUG_SCAN=15): the TMA stream alone, live on this box"},
+                                             "(NGU_EPI_DEBUG_SCAN=15, results invalid, never a throughput): the TMA stream alone, "
+                                             "live on this box - launched alone (launch_ms) and as pipelined steps "
+                                             "(pipelined_ms_per_step = the read-only ceiling `step_gbs` should be read against)"},
         }
         if strong is not None:
             line["strong"] = strong
